@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the GN-ODE rollout hot path (BASELINE.json metric: rollout node-steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (config.workload): epinions-scale rollout inference -- BASELINE.json configs[3].
+The epinions pickle is missing from the reference checkout, so the graph is the synthetic
+stand-in BA(N=75,879, m=5, seed=0); trials are the synthetic (beta, gamma, I0)
+draws of monitorer-sim.py:116-119; weights are the default nn.Linear init under seed 0.
+One "step" = one full rollout (T-1 = 39 Euler steps + encoder + decoder) of the rank's trials.
+Trials are independent -> sharded across ranks with the graph replicated, no collective on the
+data path; per-rank trial count is fixed, so scaling is "weak".
+
+Prints ONE JSON line (rank 0). value = node-steps/s with inputs resident in HBM; e2e = same
+metric through ODEBlock.forward with pinned-host input and output copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np    # noqa: E402
+import torch          # noqa: E402
+
+H = 64
+MAXTIME, DELTAT = 20, 0.5
+ALGO_BYTES_PER_NODE_STEP = 2060.0      # SURVEY 8d / BASELINE.md section 3 (fixed denominator)
+UNIT = "node-steps/s"
+METRIC = "GN-ODE rollout node-steps/s (epinions)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per step-kernel launch from the committed ncu --set full capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(trials, trial_offset):
+    from gn_ode_sir_b200 import synth
+    from oracle import gnode_oracle as orc      # only for the shared synthetic-input recipe
+    A = synth.epinions_standin(seed=0)
+    N = A.shape[0]
+    x = torch.zeros(trials, N, 3 + H, dtype=torch.float32)
+    for b in range(trials):
+        rng = np.random.RandomState(1000 + trial_offset + b)
+        seeds = rng.choice(N, 2, replace=False)
+        beta, gamma = rng.uniform(0.1, 0.5), rng.uniform(0.1, 0.5)
+        x[b, :, 0] = 1.0
+        x[b, seeds, 0] = 0.0
+        x[b, seeds, 1] = 1.0
+        x[b, :, 3], x[b, :, 4] = beta, gamma
+    return A, x, orc
+
+
+def cpu_reference_sample(A, orc, trials, n_points, repeats=1):
+    """Times the oracle port of the reference's CPU path (torch ops, per-step host-side
+    block_diag rebuild as at ode_nn_ngraph_sim.py:68-71) on a bounded sample."""
+    import scipy.sparse
+    N = A.shape[0]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = orc.default_params(H, seed=0)
+    x = torch.cat([orc.synthetic_trial(N, H, b) for b in range(trials)])
+    t = orc.time_grid(MAXTIME, DELTAT)[:n_points]
+
+    def rebuild():
+        bd = scipy.sparse.block_diag([A for _ in range(trials)])
+        return torch.LongTensor(np.vstack((bd.row, bd.col)))
+
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.forward(x, params, None, t, rebuild_index=rebuild)
+        best = min(best, time.perf_counter() - t0)
+    units = trials * N * (n_points - 1)
+    return units / best, cores, "%d trial(s) x %d Euler steps of the bench workload (%d node-steps, %.1f s)" % (
+        trials, n_points - 1, units, best)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    A, _, orc = build_workload(0, 0)
+    for _ in range(args.warmup):
+        cpu_reference_sample(A, orc, 1, 3)
+    vals, times = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        v, cores, sample = cpu_reference_sample(A, orc, args.ref_trials, args.ref_points)
+        times.append(time.perf_counter() - t0)
+        vals.append(v)
+    value = float(np.mean(vals))
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args, world),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "epinions stand-in BA(N=75879,m=5,seed=0) rollout inference, H=64, T=40 (maxTime=20, deltaT=0.5), "
+                        "%d trials per GPU (BASELINE.json configs[3])" % args.trials,
+            "trials_per_gpu": args.trials, "global_trials": args.trials * world, "nodes": 75879,
+            "euler_steps": int(len(np.arange(0, MAXTIME, DELTAT)) - 1), "parallelism": "trial-sharded dp%d, graph replicated" % world,
+            "l2_policy": "no flush: per-step working set (state+I' of all trials, >3 GB) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trials", type=int, default=128, help="trials per GPU")
+    ap.add_argument("--ref-trials", type=int, default=2)
+    ap.add_argument("--ref-points", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GN-ODE rollout has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    import gn_ode_sir_b200 as gn
+    from gn_ode_sir_b200 import _lib
+    gn.build_library()
+    L = _lib.lib()
+
+    A, x_host, orc = build_workload(args.trials, rank * args.trials)
+    N = A.shape[0]
+    T = len(np.arange(0, MAXTIME, DELTAT))
+    torch.manual_seed(0)
+    of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, H, dev)
+    blk = gn.ode_sim.ODEBlock(MAXTIME, DELTAT, N, [0, 1], H, of, dev).to(dev).eval()
+    units_per_step = args.trials * N * (T - 1)
+    rows = args.trials * N
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident measurement (value, roofline)
+    x_dev = x_host.to(dev)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            blk(x_dev)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = int(L.gnode_launch_count())
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        ev[0].record()
+        for _ in range(args.steps):
+            S, I, R = blk(x_dev)
+        ev[1].record()
+        barrier()
+        clocks = sampler.stop()
+        launches = int(L.gnode_launch_count()) - launches0
+        ms_total = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    ms_per_step = ms_total / args.steps
+    value = world * units_per_step / (ms_per_step * 1e-3)
+    # dominant kernel = the fused Euler-step kernel: (T-1) launches per rollout, each over all rows;
+    # the encoder launch (1 of T) is timed in the same stream window and is charged to the step kernel
+    # (conservative: makes the per-launch time slightly larger).
+    step_launches = args.steps * (T - 1)
+    step_ms = ev[0].elapsed_time(ev[1]) / step_launches
+    peak, peak_src = measured_peak()
+    achieved = rows * ALGO_BYTES_PER_NODE_STEP / (step_ms * 1e-3) / 1e9
+    traffic = ncu_traffic_per_launch()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "kernel": "gnode::step_kernel<MODE_STEP>", "launch_ms": step_ms, "rows_per_launch": rows,
+                "algorithmic_bytes_per_node_step": ALGO_BYTES_PER_NODE_STEP, "peak_source": peak_src}
+    del S, I, R
+
+    # ---------------- end-to-end through the public API with host buffers
+    x_pin = x_host.pin_memory()
+    out_pin = torch.empty((T, rows, 3), dtype=torch.float32).pin_memory()
+    h2d_bytes = x_pin.numel() * 4
+    d2h_bytes = out_pin.numel() * 4
+
+    def e2e_step():
+        xd = x_pin.to(dev, non_blocking=True)
+        S, I, R = blk(xd)                                  # views of one [T, M, 3] buffer
+        out_pin.copy_(S._base if S._base is not None else torch.cat((S, I, R), -1), non_blocking=True)
+
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev2[0].record()
+        for _ in range(args.steps):
+            e2e_step()
+        ev2[1].record()
+        barrier()
+        e2e_ms = max_over_ranks(ev2[0].elapsed_time(ev2[1])) / args.steps
+    e2e = {"value": world * units_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms}
+
+    # ---------------- CPU baseline (oracle port of the reference's CPU path), rank 0, N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_reference_sample(A, orc, args.ref_trials, args.ref_points)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+// Internal declarations shared by the kernels of libgnode_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gnode_b200.h"
+
+namespace gnode {
+
+constexpr int H = GNODE_H;            // hidden width (64)
+constexpr int TILE = 128;             // rows per CTA tile (== UMMA M, == TMEM lanes)
+constexpr int NTHREADS = 512;         // 16 warps per CTA
+constexpr int CHUNKS = H / 4;         // 16-byte chunks per row (16)
+
+// ---- host side ------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+#define GN_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            gnode::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                             cudaGetErrorString(e_));                              \
+            return GNODE_ERR_CUDA;                                                 \
+        }                                                                          \
+    } while (0)
+
+#define GN_LAUNCH_CHECK()                                                          \
+    do {                                                                           \
+        gnode::g_launches++;                                                       \
+        cudaError_t e_ = cudaGetLastError();                                       \
+        if (e_ != cudaSuccess) {                                                   \
+            gnode::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__,      \
+                             cudaGetErrorString(e_));                              \
+            return GNODE_ERR_CUDA;                                                 \
+        }                                                                          \
+    } while (0)
+
+}  // namespace gnode
+
+// One graph: CSR pattern (and its transpose) resident in HBM.
+struct gnode_graph {
+    int32_t n = 0;
+    int64_t nnz = 0;
+    int32_t max_degree = 0;
+    int32_t symmetric = 0;
+    int32_t* d_rowptr = nullptr;    // [n+1]
+    int32_t* d_colidx = nullptr;    // [nnz]
+    int32_t* d_rowptr_t = nullptr;  // transpose (aliases the above when symmetric)
+    int32_t* d_colidx_t = nullptr;
+    int device = 0;
+};
+
+// Device-visible description of one instance (one diagonal block).
+struct GnInstance {
+    const int32_t* rowptr;
+    const int32_t* colidx;
+    const int32_t* rowptr_t;
+    const int32_t* colidx_t;
+    int32_t row0;   // first global row
+    int32_t n;      // rows in this instance
+};
+
+struct gnode_batch {
+    int64_t M = 0;
+    int32_t n_inst = 0;
+    int32_t n_tiles = 0;
+    int64_t nnz_total = 0;
+    GnInstance* d_inst = nullptr;    // [n_inst]
+    int32_t* d_tile_inst = nullptr;  // [n_tiles] instance that owns the first row of each tile
+    int device = 0;
+    int sm_count = 0;
+};
+
+// Kernel-side view of a batch.
+struct GnBatchView {
+    const GnInstance* inst;
+    const int32_t* tile_inst;
+    int32_t n_inst;
+    int32_t n_tiles;
+    int32_t M;
+};
+
+inline GnBatchView gn_view(const gnode_batch* b) {
+    GnBatchView v;
+    v.inst = b->d_inst;
+    v.tile_inst = b->d_tile_inst;
+    v.n_inst = b->n_inst;
+    v.n_tiles = b->n_tiles;
+    v.M = (int32_t)b->M;
+    return v;
+}
+
+#ifdef __CUDACC__
+namespace gnode {
+
+// Byte offset of the 16-byte chunk c4 (0..15) of tile row r (0..127) inside a
+// 32 KB tile buffer laid out as the canonical UMMA K-major SWIZZLE_128B operand:
+// two K-blocks of 32 fp32 (128 B), each [128 rows][128 B] with 16-B chunks XORed by
+// (row & 7).  Thread-per-row and row-per-half-warp accesses are both conflict-free.
+__device__ __forceinline__ int sw_off(int r, int c4) {
+    return ((c4 >> 3) << 14) + (r << 7) + ((((c4 & 7) ^ (r & 7))) << 4);
+}
+
+__device__ __forceinline__ float4 lds4(const unsigned char* base, int off) {
+    return *reinterpret_cast<const float4*>(base + off);
+}
+__device__ __forceinline__ void sts4(unsigned char* base, int off, float4 v) {
+    *reinterpret_cast<float4*>(base + off) = v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// streaming (read-once / write-once) accesses: keep them out of L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void stg4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// sigmoid(z) = 1 / (1 + exp(-z))   (nn.Sigmoid, ode_nn_ngraph_sim.py:63)
+__device__ __forceinline__ float sigmoidf_acc(float z) {
+#ifdef GNODE_FAST_SIGMOID
+    return __fdividef(1.0f, 1.0f + __expf(-z));
+#else
+    return 1.0f / (1.0f + expf(-z));
+#endif
+}
+
+}  // namespace gnode
+#endif

@@ -1,0 +1,387 @@
+// Forward rollout: encoder, fused Euler-step kernel, decoder (a1-a9).
+//
+// One CTA owns a tile of 128 consecutive rows of the batch ((trial, node) pairs) and
+// runs, per Euler step k (reference lines in brackets, ode_nn_ngraph_sim.py):
+//   1. S_k tile  -> shared memory (UMMA K-major SWIZZLE_128B layout)
+//   2. S' = sigmoid(S_k W^T + b)                        [:62-63]   -> shared memory
+//   3. row-per-half-warp: AI = sum_nbrs I'_k            [:73]      (I'_k from HBM/L2)
+//        dS,dI,dR ; y_{k+1} = y_k + dt f                [:75-77,96; torchdiffeq Euler]
+//        -> HBM (coalesced); I_{k+1} stays in shared memory; decoder + softmax of
+//        y_{k+1} -> probs[k+1]                          [:170-188]
+//   4. I'_{k+1} = sigmoid(I_{k+1} W^T + b) -> HBM       (next step's aggregation operand)
+// so one launch per step reads S,I,R,I' and writes S,I,R,I',probs exactly once; the
+// grid-wide dependency (all of I'_k before any aggregation) is the launch boundary.
+// The reference's R' = sigmoid(linear(R)) is never used (:66 vs :75-77) and is skipped.
+#include <algorithm>
+
+#include "gnode_common.cuh"
+
+namespace gnode {
+
+enum { MODE_STEP = 0, MODE_ENCODE = 1, MODE_IP = 2, MODE_RHS = 3 };
+
+struct StepArgs {
+    GnBatchView bv;
+    const float* y_in;    // [3][M][H]
+    float* y_out;         // [3][M][H]  STEP: y_{k+1}; ENCODE: y_0; RHS: f(y)
+    const float* ip_in;   // [M][H]     I'_k
+    float* ip_out;        // [M][H]     I'_{k+1}
+    float* beta;          // [M]
+    float* gamma;         // [M]
+    const float* x;       // ENCODE: [M][ldx]
+    int64_t ldx;
+    float* probs;         // [M][3] slice of the produced state, or null
+    float dt;
+    gnode_params_t p;
+};
+
+// shared-memory carve-up (bytes)
+constexpr int SM_X = 0;                        // 32 KB  operand tile (S_k, then I_{k+1})
+constexpr int SM_SP = 32768;                   // 32 KB  S' tile, then I'_{k+1} staging
+constexpr int SM_W = 65536;                    // 16 KB  W [h][k] row-major
+constexpr int SM_B = SM_W + H * H * 4;         // bias [64]
+constexpr int SM_W3 = SM_B + H * 4;            // linear3.weight [4][64]
+constexpr int SM_W1 = SM_W3 + 4 * H * 4;       // linearS1.weight [64]
+constexpr int SM_B1 = SM_W1 + H * 4;           // linearS1.bias [64]
+constexpr int SM_SMALL = SM_B1 + H * 4;        // b3[4], w2[4], b2[1]
+constexpr int SM_TOTAL = SM_SMALL + 64;
+
+// Z = X W^T (X: swizzled 128x64 tile, W: [h][k]) ; dst = sigmoid(Z + b), swizzled.
+// 256 threads: thread (r0 = tid&63, q = tid>>6) owns rows r0, r0+64 x columns [16q,16q+16).
+__device__ __forceinline__ void gemm_sigmoid(const unsigned char* Xs, const float* Ws, const float* bs,
+                                             unsigned char* dst, int tid) {
+    if (tid >= 256) return;
+    const int r0 = tid & 63, q = tid >> 6;
+    float a0[16], a1[16];
+#pragma unroll
+    for (int h = 0; h < 16; ++h) { a0[h] = 0.f; a1[h] = 0.f; }
+    const float* wq = Ws + (16 * q) * H;
+#pragma unroll 2
+    for (int c4 = 0; c4 < CHUNKS; ++c4) {
+        const float4 xa = lds4(Xs, sw_off(r0, c4));
+        const float4 xb = lds4(Xs, sw_off(r0 + 64, c4));
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const float4 w = *reinterpret_cast<const float4*>(wq + h * H + 4 * c4);
+            a0[h] = fmaf(xa.x, w.x, a0[h]); a0[h] = fmaf(xa.y, w.y, a0[h]);
+            a0[h] = fmaf(xa.z, w.z, a0[h]); a0[h] = fmaf(xa.w, w.w, a0[h]);
+            a1[h] = fmaf(xb.x, w.x, a1[h]); a1[h] = fmaf(xb.y, w.y, a1[h]);
+            a1[h] = fmaf(xb.z, w.z, a1[h]); a1[h] = fmaf(xb.w, w.w, a1[h]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * q + 4 * j);
+        float4 o0, o1;
+        o0.x = sigmoidf_acc(a0[4 * j + 0] + bb.x); o0.y = sigmoidf_acc(a0[4 * j + 1] + bb.y);
+        o0.z = sigmoidf_acc(a0[4 * j + 2] + bb.z); o0.w = sigmoidf_acc(a0[4 * j + 3] + bb.w);
+        o1.x = sigmoidf_acc(a1[4 * j + 0] + bb.x); o1.y = sigmoidf_acc(a1[4 * j + 1] + bb.y);
+        o1.z = sigmoidf_acc(a1[4 * j + 2] + bb.z); o1.w = sigmoidf_acc(a1[4 * j + 3] + bb.w);
+        sts4(dst, sw_off(r0, 4 * q + j), o0);
+        sts4(dst, sw_off(r0 + 64, 4 * q + j), o1);
+    }
+}
+
+// coalesced HBM rows -> swizzled tile (rows past M are zero-filled)
+__device__ __forceinline__ void load_tile(unsigned char* dst, const float* src, int64_t tile0, int M, int tid) {
+    for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
+        const int rr = idx >> 4, c4 = idx & 15;
+        const int64_t g = tile0 + rr;
+        if (g < M) cp_async16(dst + sw_off(rr, c4), src + (size_t)g * H + 4 * c4);
+        else sts4(dst, sw_off(rr, c4), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    cp_async_wait_all();
+}
+
+__device__ __forceinline__ void store_tile(float* dst, const unsigned char* src, int64_t tile0, int M, int tid) {
+    for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
+        const int rr = idx >> 4, c4 = idx & 15;
+        const int64_t g = tile0 + rr;
+        if (g < M) stg4(dst + (size_t)g * H + 4 * c4, lds4(src, sw_off(rr, c4)));
+    }
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+// decoder + softmax of one row held 4 channels per lane by a half-warp
+// (linear3 -> ReLU -> linearS2 -> softmax over {S,I,R}; ode_nn_ngraph_sim.py:172-187)
+__device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const float* W3s, const float* small,
+                                           int l, bool valid, float* probs_row) {
+    float v[12];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const float4 w = *reinterpret_cast<const float4*>(W3s + m * H + 4 * l);
+        v[m] = dot4(s, w); v[4 + m] = dot4(i, w); v[8 + m] = dot4(r, w);
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1)
+#pragma unroll
+        for (int m = 0; m < 12; ++m) v[m] += __shfl_xor_sync(0xffffffffu, v[m], off);
+    if (l == 0 && valid) {
+        const float* b3 = small; const float* w2 = small + 4; const float b2 = small[8];
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float acc = b2;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc = fmaf(w2[m], fmaxf(v[4 * c + m] + b3[m], 0.f), acc);
+            o[c] = acc;
+        }
+        const float mx = fmaxf(o[0], fmaxf(o[1], o[2]));
+        const float e0 = expf(o[0] - mx), e1 = expf(o[1] - mx), e2 = expf(o[2] - mx);
+        const float inv = 1.0f / (e0 + e1 + e2);
+        probs_row[0] = e0 * inv; probs_row[1] = e1 * inv; probs_row[2] = e2 * inv;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* Xs = smem + SM_X;
+    unsigned char* SPs = smem + SM_SP;
+    float* Ws = reinterpret_cast<float*>(smem + SM_W);
+    float* bs = reinterpret_cast<float*>(smem + SM_B);
+    float* W3s = reinterpret_cast<float*>(smem + SM_W3);
+    float* w1s = reinterpret_cast<float*>(smem + SM_W1);
+    float* b1s = reinterpret_cast<float*>(smem + SM_B1);
+    float* small = reinterpret_cast<float*>(smem + SM_SMALL);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int l = tid & 15;           // 16-byte chunk of the row owned in the row-per-half-warp phases
+    const int hw = tid >> 4;          // half-warp id 0..31
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+
+    // parameters -> shared memory (once per CTA; the CTA is persistent over its tiles)
+    for (int i = tid; i < H * H / 4; i += NTHREADS)
+        reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    if (MODE == MODE_ENCODE && tid < H) { w1s[tid] = a.p.s1_w[tid]; b1s[tid] = a.p.s1_b[tid]; }
+    if (MODE == MODE_ENCODE || MODE == MODE_STEP) {     // decoder weights (RHS / IP callers pass none)
+        if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
+        if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+        if (tid == 0) small[8] = a.p.s2_b[0];
+    }
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TILE;
+
+        if (MODE == MODE_STEP || MODE == MODE_RHS) {
+            load_tile(Xs, a.y_in, tile0, M, tid);                 // S_k
+            __syncthreads();
+            gemm_sigmoid(Xs, Ws, bs, SPs, tid);                   // S'
+            __syncthreads();
+        } else if (MODE == MODE_IP) {
+            load_tile(Xs, a.y_in + plane, tile0, M, tid);         // I
+            __syncthreads();
+        }
+
+        if (MODE == MODE_STEP || MODE == MODE_RHS) {
+            int inst = a.bv.tile_inst[tile];
+#pragma unroll 1
+            for (int it = 0; it < TILE / 32; ++it) {
+                const int rr = hw + 32 * it;
+                const int64_t g = tile0 + rr;
+                const bool valid = g < M;
+                int row0 = 0, e0 = 0, deg = 0;
+                const int32_t* ci = nullptr;
+                if (valid) {
+                    while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                    const GnInstance I = a.bv.inst[inst];
+                    row0 = I.row0; ci = I.colidx;
+                    const int n = (int)(g - row0);
+                    e0 = I.rowptr[n];
+                    deg = I.rowptr[n + 1] - e0;
+                }
+                const int degmax = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
+                // ---- aggregation: sequential ascending-column sum, 8 rows in flight per lane
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int eb = 0; eb < degmax; eb += 16) {
+                    const int mine = (eb + l < deg) ? ci[e0 + eb + l] + row0 : -1;
+#pragma unroll
+                    for (int jb = 0; jb < 16; jb += 8) {
+                        if (eb + jb < degmax) {
+                            float4 v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int c = __shfl_sync(0xffffffffu, mine, (lane & 16) + jb + j);
+                                v[j] = (c >= 0) ? ldg4(a.ip_in + (size_t)c * H + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+                        }
+                    }
+                }
+                // ---- SIR derivative + Euler update (explicit _rn ops: no FMA contraction, the
+                //      reference rounds after every ATen op)
+                float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
+                if (valid) {
+                    const size_t off = (size_t)g * H + 4 * l;
+                    const float4 ipo = ldg4(a.ip_in + off);
+                    const float4 s = lds4(Xs, sw_off(rr, l));
+                    const float4 sp = lds4(SPs, sw_off(rr, l));
+                    const float4 iv = ldg4_stream(a.y_in + plane + off);
+                    const float4 rv = ldg4_stream(a.y_in + 2 * plane + off);
+                    const float nbe = -a.beta[g], ga = a.gamma[g], dt = a.dt;
+#define GN_COMP(c)                                                                  \
+    {                                                                               \
+        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
+        const float dR = __fmul_rn(ga, ipo.c);                                      \
+        const float dI = __fsub_rn(-dS, dR);                                        \
+        if (MODE == MODE_RHS) { sn.c = dS; in_.c = dI; rn.c = dR; }                 \
+        else {                                                                      \
+            sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                               \
+            in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                             \
+            rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                              \
+        }                                                                           \
+    }
+                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+#undef GN_COMP
+                    stg4_stream(a.y_out + off, sn);
+                    stg4_stream(a.y_out + plane + off, in_);
+                    stg4_stream(a.y_out + 2 * plane + off, rn);
+                    if (MODE == MODE_STEP) sts4(Xs, sw_off(rr, l), in_);      // operand of the next GEMM
+                }
+                if (MODE == MODE_STEP && a.probs != nullptr)
+                    decode_row(sn, in_, rn, W3s, small, l, valid, a.probs + (size_t)(valid ? g : 0) * 3);
+            }
+            __syncthreads();
+        } else if (MODE == MODE_ENCODE) {
+            // encoder: C0 = relu(c * w1 + b1) for c in {S0, I0, R0}  (ode_nn_ngraph_sim.py:151-156)
+#pragma unroll 1
+            for (int it = 0; it < TILE / 32; ++it) {
+                const int rr = hw + 32 * it;
+                const int64_t g = tile0 + rr;
+                const bool valid = g < M;
+                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), i0 = s0, r0 = s0;
+                if (valid) {
+                    const float* xr = a.x + (size_t)g * a.ldx;
+                    const float cs = xr[0], ci_ = xr[1], cr = xr[2];
+                    if (l == 0) { a.beta[g] = xr[3]; a.gamma[g] = xr[4]; }
+                    const float4 w = *reinterpret_cast<const float4*>(w1s + 4 * l);
+                    const float4 b = *reinterpret_cast<const float4*>(b1s + 4 * l);
+#define GN_ENC(c)                                                             \
+    s0.c = fmaxf(__fadd_rn(__fmul_rn(cs, w.c), b.c), 0.f);                    \
+    i0.c = fmaxf(__fadd_rn(__fmul_rn(ci_, w.c), b.c), 0.f);                   \
+    r0.c = fmaxf(__fadd_rn(__fmul_rn(cr, w.c), b.c), 0.f);
+                    GN_ENC(x) GN_ENC(y) GN_ENC(z) GN_ENC(w)
+#undef GN_ENC
+                    const size_t off = (size_t)g * H + 4 * l;
+                    stg4_stream(a.y_out + off, s0);
+                    stg4_stream(a.y_out + plane + off, i0);
+                    stg4_stream(a.y_out + 2 * plane + off, r0);
+                }
+                sts4(Xs, sw_off(rr, l), i0);
+                if (a.probs != nullptr)
+                    decode_row(s0, i0, r0, W3s, small, l, valid, a.probs + (size_t)(valid ? g : 0) * 3);
+            }
+            __syncthreads();
+        }
+
+        if (MODE != MODE_RHS) {
+            gemm_sigmoid(Xs, Ws, bs, SPs, tid);                   // I'_{k+1}
+            __syncthreads();
+            store_tile(a.ip_out, SPs, tile0, M, tid);
+            __syncthreads();
+        }
+    }
+}
+
+template <int MODE>
+static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        GN_CUDA(cudaFuncSetAttribute(step_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        configured = true;
+    }
+    const int grid = std::min(b->n_tiles, 2 * b->sm_count);
+    step_kernel<MODE><<<grid, NTHREADS, SM_TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace gnode
+
+using namespace gnode;
+
+extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) {
+    if (!b) return 0;
+    const size_t M = (size_t)b->M;
+    size_t bytes = 2 * align_up(M * sizeof(float), 256);          // beta, gamma
+    bytes += 2 * align_up(M * H * sizeof(float), 256);            // I' ping-pong
+    if (!with_traj) bytes += 2 * align_up(3 * M * H * sizeof(float), 256);  // state ping-pong
+    return bytes;
+}
+
+extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                     int32_t T, const float* dt_host, float* traj, float* probs,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!b || !x || !p || !probs || !workspace || T < 1 || ldx < 5 || (T > 1 && !dt_host)) {
+        set_error("gnode_rollout_forward: bad arguments (T=%d ldx=%lld)", T, (long long)ldx);
+        return GNODE_ERR_ARG;
+    }
+    if (workspace_bytes < gnode_rollout_workspace_bytes(b, traj != nullptr)) {
+        set_error("gnode_rollout_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                  gnode_rollout_workspace_bytes(b, traj != nullptr));
+        return GNODE_ERR_ARG;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t M = (size_t)b->M;
+    unsigned char* ws = (unsigned char*)workspace;
+    float* beta = (float*)ws;  ws += align_up(M * sizeof(float), 256);
+    float* gamma = (float*)ws; ws += align_up(M * sizeof(float), 256);
+    float* ip[2];
+    ip[0] = (float*)ws; ws += align_up(M * H * sizeof(float), 256);
+    ip[1] = (float*)ws; ws += align_up(M * H * sizeof(float), 256);
+    float* st[2] = {nullptr, nullptr};
+    if (!traj) {
+        st[0] = (float*)ws; ws += align_up(3 * M * H * sizeof(float), 256);
+        st[1] = (float*)ws;
+    }
+    auto state = [&](int k) -> float* { return traj ? traj + (size_t)k * 3 * M * H : st[k & 1]; };
+
+    StepArgs a;
+    a.bv = gn_view(b);
+    a.p = *p;
+    a.beta = beta; a.gamma = gamma;
+    a.x = x; a.ldx = ldx;
+    a.y_in = nullptr; a.ip_in = nullptr;
+    a.y_out = state(0); a.ip_out = ip[0];
+    a.probs = probs; a.dt = 0.f;
+    int rc = launch_step<MODE_ENCODE>(b, a, stream);
+    if (rc) return rc;
+    for (int k = 0; k + 1 < T; ++k) {
+        a.y_in = state(k); a.y_out = state(k + 1);
+        a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
+        a.probs = probs + (size_t)(k + 1) * M * 3;
+        a.dt = dt_host[k];
+        rc = launch_step<MODE_STEP>(b, a, stream);
+        if (rc) return rc;
+    }
+    return GNODE_OK;
+}
+
+extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* beta, const float* gamma,
+                                  const gnode_params_t* p, float* dy, float* scratch, void* stream_) {
+    if (!b || !y || !beta || !gamma || !p || !dy || !scratch) {
+        set_error("gnode_odefunc_eval: null argument");
+        return GNODE_ERR_ARG;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    StepArgs a;
+    a.bv = gn_view(b);
+    a.p = *p;
+    a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f;
+    a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
+    int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
+    if (rc) return rc;
+    a.ip_in = scratch; a.ip_out = nullptr; a.y_out = dy;
+    return launch_step<MODE_RHS>(b, a, stream);
+}

@@ -1,0 +1,198 @@
+// Graph / batch handles and the standalone neighbour aggregation (a6, a7).
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+
+#include "gnode_common.cuh"
+
+namespace gnode {
+
+static thread_local char t_err[1024] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+// out[r, :] = sum_{c in adj(r)} in[c, :]  -- one half-warp per row, 16 B per lane, the
+// neighbours of a row are accumulated sequentially in ascending-column order
+// (the order of the reference's CPU scatter_add_, ode_nn_ngraph_sim.py:73).
+__global__ void __launch_bounds__(256) aggregate_kernel(GnBatchView bv, const float* __restrict__ in,
+                                                         float* __restrict__ out, int transpose) {
+    const int l = threadIdx.x & 15;
+    const int hw_in_block = threadIdx.x >> 4;
+    const int hw_per_block = blockDim.x >> 4;
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+    for (int64_t r = (int64_t)blockIdx.x * hw_per_block + hw_in_block; r < bv.M;
+         r += (int64_t)gridDim.x * hw_per_block) {
+        // instance lookup: binary search over row0 (n_inst is small and cached)
+        int lo = 0, hi = bv.n_inst - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (bv.inst[mid].row0 <= r) lo = mid; else hi = mid - 1;
+        }
+        const GnInstance I = bv.inst[lo];
+        const int32_t* rp = transpose ? I.rowptr_t : I.rowptr;
+        const int32_t* ci = transpose ? I.colidx_t : I.colidx;
+        const int n = (int)(r - I.row0);
+        const int e0 = rp[n], e1 = rp[n + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = e0; e < e1; e += 16) {
+            const int mine = (e + l < e1) ? ci[e + l] : 0;
+            const int cnt = min(16, e1 - e);
+            for (int j = 0; j < cnt; ++j) {
+                const int c = __shfl_sync(hmask, mine, j, 16) + I.row0;
+                const float4 v = ldg4(in + (size_t)c * H + 4 * l);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        stg4(out + (size_t)r * H + 4 * l, acc);
+    }
+}
+
+}  // namespace gnode
+
+using namespace gnode;
+
+extern "C" const char* gnode_last_error(void) { return t_err; }
+extern "C" int gnode_version(void) { return 100; }
+extern "C" int64_t gnode_launch_count(void) { return g_launches; }
+
+extern "C" int gnode_graph_create(int32_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                                  gnode_graph_t* out) {
+    if (!out || !rowptr || (nnz > 0 && !colidx) || n <= 0 || nnz < 0 || nnz > 0x7fffffffLL) {
+        set_error("gnode_graph_create: bad arguments (n=%d nnz=%lld)", n, (long long)nnz);
+        return GNODE_ERR_ARG;
+    }
+    if (rowptr[0] != 0 || rowptr[n] != nnz) {
+        set_error("gnode_graph_create: rowptr[0]=%d rowptr[n]=%d do not match nnz=%lld", rowptr[0], rowptr[n],
+                  (long long)nnz);
+        return GNODE_ERR_ARG;
+    }
+    std::vector<int32_t> ci(colidx, colidx + nnz);
+    int32_t maxdeg = 0;
+    for (int32_t r = 0; r < n; ++r) {
+        if (rowptr[r + 1] < rowptr[r]) {
+            set_error("gnode_graph_create: rowptr not monotone at row %d", r);
+            return GNODE_ERR_ARG;
+        }
+        std::sort(ci.begin() + rowptr[r], ci.begin() + rowptr[r + 1]);
+        maxdeg = std::max(maxdeg, rowptr[r + 1] - rowptr[r]);
+    }
+    for (int64_t e = 0; e < nnz; ++e)
+        if (ci[e] < 0 || ci[e] >= n) {
+            set_error("gnode_graph_create: column index %d out of range at entry %lld", ci[e], (long long)e);
+            return GNODE_ERR_ARG;
+        }
+    // transpose pattern by counting sort (rows ascending -> columns of A^T ascending)
+    std::vector<int32_t> rpt(n + 1, 0), cit(nnz);
+    for (int64_t e = 0; e < nnz; ++e) rpt[ci[e] + 1]++;
+    for (int32_t r = 0; r < n; ++r) rpt[r + 1] += rpt[r];
+    {
+        std::vector<int32_t> fill(rpt.begin(), rpt.end() - 1);
+        for (int32_t r = 0; r < n; ++r)
+            for (int32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) cit[fill[ci[e]]++] = r;
+    }
+    const bool sym = (memcmp(rpt.data(), rowptr, sizeof(int32_t) * (n + 1)) == 0) &&
+                     (nnz == 0 || memcmp(cit.data(), ci.data(), sizeof(int32_t) * nnz) == 0);
+
+    gnode_graph* g = new gnode_graph();
+    g->n = n; g->nnz = nnz; g->max_degree = maxdeg; g->symmetric = sym ? 1 : 0;
+    GN_CUDA(cudaGetDevice(&g->device));
+    const size_t nnz_alloc = (size_t)std::max<int64_t>(nnz, 1);
+    GN_CUDA(cudaMalloc(&g->d_rowptr, sizeof(int32_t) * (n + 1)));
+    GN_CUDA(cudaMalloc(&g->d_colidx, sizeof(int32_t) * nnz_alloc));
+    GN_CUDA(cudaMemcpy(g->d_rowptr, rowptr, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice));
+    if (nnz) GN_CUDA(cudaMemcpy(g->d_colidx, ci.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+    if (sym) {
+        g->d_rowptr_t = g->d_rowptr;
+        g->d_colidx_t = g->d_colidx;
+    } else {
+        GN_CUDA(cudaMalloc(&g->d_rowptr_t, sizeof(int32_t) * (n + 1)));
+        GN_CUDA(cudaMalloc(&g->d_colidx_t, sizeof(int32_t) * nnz_alloc));
+        GN_CUDA(cudaMemcpy(g->d_rowptr_t, rpt.data(), sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice));
+        if (nnz) GN_CUDA(cudaMemcpy(g->d_colidx_t, cit.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+    }
+    *out = g;
+    return GNODE_OK;
+}
+
+extern "C" int gnode_graph_destroy(gnode_graph_t g) {
+    if (!g) return GNODE_OK;
+    if (!g->symmetric) {
+        cudaFree(g->d_rowptr_t);
+        cudaFree(g->d_colidx_t);
+    }
+    cudaFree(g->d_rowptr);
+    cudaFree(g->d_colidx);
+    delete g;
+    return GNODE_OK;
+}
+
+extern "C" int gnode_graph_info(gnode_graph_t g, int32_t* n, int64_t* nnz, int32_t* max_degree, int32_t* symmetric) {
+    if (!g) { set_error("gnode_graph_info: null graph"); return GNODE_ERR_ARG; }
+    if (n) *n = g->n;
+    if (nnz) *nnz = g->nnz;
+    if (max_degree) *max_degree = g->max_degree;
+    if (symmetric) *symmetric = g->symmetric;
+    return GNODE_OK;
+}
+
+extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_inst, gnode_batch_t* out) {
+    if (!out || !inst_graphs || n_inst <= 0) {
+        set_error("gnode_batch_create: bad arguments (n_inst=%d)", n_inst);
+        return GNODE_ERR_ARG;
+    }
+    std::vector<GnInstance> inst(n_inst);
+    int64_t M = 0, nnz = 0;
+    for (int32_t i = 0; i < n_inst; ++i) {
+        const gnode_graph* g = inst_graphs[i];
+        if (!g) { set_error("gnode_batch_create: instance %d has a null graph", i); return GNODE_ERR_ARG; }
+        inst[i].rowptr = g->d_rowptr; inst[i].colidx = g->d_colidx;
+        inst[i].rowptr_t = g->d_rowptr_t; inst[i].colidx_t = g->d_colidx_t;
+        inst[i].row0 = (int32_t)M; inst[i].n = g->n;
+        M += g->n; nnz += g->nnz;
+        if (M > 0x7fffff00LL) { set_error("gnode_batch_create: %lld rows exceed the int32 row space", (long long)M); return GNODE_ERR_ARG; }
+    }
+    gnode_batch* b = new gnode_batch();
+    b->M = M; b->n_inst = n_inst; b->nnz_total = nnz;
+    b->n_tiles = (int32_t)((M + TILE - 1) / TILE);
+    std::vector<int32_t> tile_inst(b->n_tiles);
+    int32_t cur = 0;
+    for (int32_t t = 0; t < b->n_tiles; ++t) {
+        const int64_t r = (int64_t)t * TILE;
+        while (cur + 1 < n_inst && inst[cur + 1].row0 <= r) ++cur;
+        tile_inst[t] = cur;
+    }
+    GN_CUDA(cudaGetDevice(&b->device));
+    GN_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
+    GN_CUDA(cudaMalloc(&b->d_inst, sizeof(GnInstance) * n_inst));
+    GN_CUDA(cudaMalloc(&b->d_tile_inst, sizeof(int32_t) * b->n_tiles));
+    GN_CUDA(cudaMemcpy(b->d_inst, inst.data(), sizeof(GnInstance) * n_inst, cudaMemcpyHostToDevice));
+    GN_CUDA(cudaMemcpy(b->d_tile_inst, tile_inst.data(), sizeof(int32_t) * b->n_tiles, cudaMemcpyHostToDevice));
+    *out = b;
+    return GNODE_OK;
+}
+
+extern "C" int gnode_batch_destroy(gnode_batch_t b) {
+    if (!b) return GNODE_OK;
+    cudaFree(b->d_inst);
+    cudaFree(b->d_tile_inst);
+    delete b;
+    return GNODE_OK;
+}
+
+extern "C" int64_t gnode_batch_rows(gnode_batch_t b) { return b ? b->M : -1; }
+
+extern "C" int gnode_aggregate(gnode_batch_t b, const float* in, float* out, int transpose, void* stream) {
+    if (!b || !in || !out) { set_error("gnode_aggregate: null argument"); return GNODE_ERR_ARG; }
+    const int hw_per_block = 256 / 16;
+    int64_t blocks = (b->M + hw_per_block - 1) / hw_per_block;
+    blocks = std::min<int64_t>(blocks, (int64_t)b->sm_count * 16);
+    aggregate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gn_view(b), in, out, transpose);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}

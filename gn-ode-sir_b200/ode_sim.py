@@ -1,0 +1,99 @@
+"""Drop-in ``ODEfunc`` / ``ODEBlock`` for the single-graph / many-trials script.
+
+Same constructors, ``forward`` signatures, parameter names / shapes / default
+initialisation order as /root/reference/ode_nn_ngraph_sim.py:37-96 (ODEfunc) and
+:99-188 (ODEBlock), so ``ode_nn_ngraph_sim.py``'s ``train`` / ``test`` / ``main``
+(and therefore ``monitorer-sim.py``) run unchanged and ``state_dict``s interchange.
+The arithmetic runs in hand-written sm_100a kernels behind the C ABI.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import rollout as _ro
+from .graph import BatchCache, DeviceGraph
+
+
+class ODEfunc(nn.Module):
+    """Right-hand side holder: owns ``linear`` (H->H) and the unused ``ln``."""
+
+    def __init__(self, A, beta, gamma, hidden1, device):
+        super().__init__()
+        if hidden1 != _ro.H:
+            raise NotImplementedError("the B200 kernels are specialised for hidden width %d (got %d)" % (_ro.H, hidden1))
+        self.A = A
+        self.beta = beta
+        self.gamma = gamma
+        # construction order == reference (LayerNorm draws no random numbers, Linear does)
+        self.ln = nn.LayerNorm(hidden1)
+        self.linear = nn.Linear(hidden1, hidden1)
+        self.relu = nn.ReLU()
+        self.sigmoid = nn.Sigmoid()
+        self.dropout = nn.Dropout(0.1)
+        self._graph = None
+        self._batches = BatchCache()
+
+    # -- device graph management ------------------------------------------
+    def device_graph(self):
+        if self._graph is None:
+            self._graph = DeviceGraph(self.A)
+        return self._graph
+
+    def batch_for(self, n_trials):
+        g = self.device_graph()
+        return self._batches.get([g] * n_trials)
+
+    def forward(self, t, x):
+        """f(t, y) on the packed state y = cat(S, I, R, bg) of shape [4M, H]
+        (ode_nn_ngraph_sim.py:58-96). Inference-only entry: ODEBlock.forward runs the
+        whole rollout in one fused call and never comes through here."""
+        M = x.size(0) // 4
+        N = self.device_graph().n
+        batch = self.batch_for(M // N)
+        y = x[:3 * M].view(3, M, x.size(1))
+        bg = x[3 * M:]
+        dy = _ro.odefunc_eval(y, bg[:, 0], bg[:, 1], batch,
+                              [self.linear.weight, self.linear.bias] + [self.linear.bias] * 6)
+        return torch.cat((dy.view(3 * M, -1), torch.zeros_like(bg)))
+
+
+class ODEBlock(nn.Module):
+    """Encoder -> fixed-grid Euler rollout -> decoder -> softmax, one fused rollout."""
+
+    grad_mode = "adjoint"      # what the reference trains with (torchdiffeq odeint_adjoint)
+
+    def __init__(self, maxTime, deltaT, n_nodes, indices, hidden1, odefunc, device):
+        super().__init__()
+        self.maxTime = maxTime
+        self.deltaT = deltaT
+        self.device = device
+        self.integration_time = torch.from_numpy(np.arange(0, self.maxTime, self.deltaT)).to(device)
+        self.odefunc = odefunc
+        self.n_nodes = n_nodes
+        self.indices = torch.tensor(indices, requires_grad=False)
+        self.hidden1 = hidden1
+        self.linearS1 = nn.Linear(1, hidden1)
+        self.ln = nn.LayerNorm(hidden1)
+        self.linear3 = nn.Linear(hidden1, 4)
+        self.relu3 = nn.ReLU()
+        self.linearS2 = nn.Linear(4, 1)
+        self.softmax = nn.Softmax(dim=2)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(0.2)
+        self._dt = _ro.dt_array(self.integration_time)
+
+    def _params(self):
+        return [self.odefunc.linear.weight, self.odefunc.linear.bias, self.linearS1.weight, self.linearS1.bias,
+                self.linear3.weight, self.linear3.bias, self.linearS2.weight, self.linearS2.bias]
+
+    def forward(self, x):
+        x = x.view(-1, x.size(2))                      # [B*N, 3+H]
+        n_trials = x.size(0) // self.odefunc.device_graph().n
+        batch = self.odefunc.batch_for(n_trials)
+        probs = _ro.rollout(x, batch, self._dt, self._params(), self.grad_mode)   # [T, M, 3]
+        # adjoint parameters that never enter f get ZERO gradients in the reference (torchdiffeq
+        # returns zeros for unused adjoint params): keep Adam's view of odefunc.ln identical
+        if probs.requires_grad:
+            probs = probs + 0.0 * (self.odefunc.ln.weight.sum() + self.odefunc.ln.bias.sum())
+        S, I, R = probs.chunk(3, dim=-1)               # each [T, M, 1]
+        return S, I, R

@@ -1,0 +1,12 @@
+"""Import shim: ``import gn_ode_sir_b200`` loads the package directory ``gn-ode-sir_b200/``
+(a hyphen is not importable) and replaces this module with it."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gn-ode-sir_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_pkg = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _pkg
+_spec.loader.exec_module(_pkg)

@@ -1,0 +1,140 @@
+/*
+ * gnode_b200.h -- C ABI of the B200-native GN-ODE rollout library (libgnode_b200.so).
+ *
+ * The reference (sissykosm/GN-ODE-SIR) is pure Python and has no FFI; its boundary
+ * for this path is the Python class interface ODEfunc / ODEBlock.  Every entry
+ * point below names the reference code it replaces (paths relative to the reference
+ * root).  The Python drop-in classes in gn-ode-sir_b200/ bind these symbols with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - all tensors are caller-allocated DEVICE memory, fp32, row-major, H == 64;
+ *   - the library owns only graph/batch handles (device CSR + tiny descriptors);
+ *   - every call takes the CUDA stream to enqueue on; no call synchronises the
+ *     stream or the device (graph/batch creation use their own blocking copies);
+ *   - return value 0 on success, negative on error; gnode_last_error() returns a
+ *     thread-local description of the most recent failure;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Row space: a "batch" is a list of instances (one graph + one trial each).
+ * Instance i owns the contiguous global rows [row0_i, row0_i + n_i); M = sum n_i.
+ * This is the reference's block-diagonal batching
+ *   ode_nn_ngraph_sim.py:68-71  (B copies of one graph, rows b*N + n)
+ *   ode_nn_ngraphs.py:65-71     (ragged concatenation of different graphs).
+ */
+#ifndef GNODE_B200_H
+#define GNODE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNODE_H 64              /* hidden width the kernels are specialised for */
+#define GNODE_OK 0
+#define GNODE_ERR_ARG (-1)
+#define GNODE_ERR_CUDA (-2)
+#define GNODE_ERR_UNSUPPORTED (-3)
+
+typedef struct gnode_graph* gnode_graph_t;
+typedef struct gnode_batch* gnode_batch_t;
+
+/* Device pointers to the model parameters; names are the reference's state_dict
+ * keys (ode_nn_ngraph_sim.py:47-48,123-131).  The two unused LayerNorms have no
+ * arithmetic on the path and are not passed. */
+typedef struct {
+    const float* lin_w;   /* odefunc.linear.weight [H,H] (out,in)           */
+    const float* lin_b;   /* odefunc.linear.bias   [H]                       */
+    const float* s1_w;    /* linearS1.weight       [H,1] -> H contiguous     */
+    const float* s1_b;    /* linearS1.bias         [H]                       */
+    const float* l3_w;    /* linear3.weight        [4,H]                     */
+    const float* l3_b;    /* linear3.bias          [4]                       */
+    const float* s2_w;    /* linearS2.weight       [1,4] -> 4 contiguous     */
+    const float* s2_b;    /* linearS2.bias         [1]                       */
+} gnode_params_t;
+
+/* Flat layout of the gradient vector written by gnode_rollout_backward
+ * (same order as gnode_params_t). */
+#define GNODE_GRAD_OFF_LIN_W 0
+#define GNODE_GRAD_OFF_LIN_B (GNODE_H * GNODE_H)
+#define GNODE_GRAD_OFF_S1_W (GNODE_GRAD_OFF_LIN_B + GNODE_H)
+#define GNODE_GRAD_OFF_S1_B (GNODE_GRAD_OFF_S1_W + GNODE_H)
+#define GNODE_GRAD_OFF_L3_W (GNODE_GRAD_OFF_S1_B + GNODE_H)
+#define GNODE_GRAD_OFF_L3_B (GNODE_GRAD_OFF_L3_W + 4 * GNODE_H)
+#define GNODE_GRAD_OFF_S2_W (GNODE_GRAD_OFF_L3_B + 4)
+#define GNODE_GRAD_OFF_S2_B (GNODE_GRAD_OFF_S2_W + 4)
+#define GNODE_GRAD_COUNT (GNODE_GRAD_OFF_S2_B + 1)
+
+#define GNODE_GRAD_ADJOINT 0   /* torchdiffeq odeint_adjoint semantics (what the reference trains with) */
+#define GNODE_GRAD_DISCRETE 1  /* exact back-propagation of the discrete Euler loop */
+
+const char* gnode_last_error(void);
+int gnode_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t gnode_launch_count(void);
+
+/* ---- graphs ---------------------------------------------------------------
+ * Replaces the host-resident scipy CSR the reference keeps in ODEfunc.A /
+ * ODEfunc.A_list (ode_nn_ngraph_sim.py:41, ode_nn_ngraphs.py:41, built by
+ * nx.adjacency_matrix at ode_nn.py:413) and its per-step re-expansion to COO.
+ * rowptr[n+1], colidx[nnz] are HOST int32 CSR arrays; stored values are ignored
+ * (every stored entry counts once, as in the reference). Columns are sorted per
+ * row at creation so the neighbour sum runs in ascending-column order, the order
+ * of the reference's CPU scatter_add_. The transposed pattern is built here too
+ * (backward); undirected graphs share one copy. */
+int gnode_graph_create(int32_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                       gnode_graph_t* out);
+int gnode_graph_destroy(gnode_graph_t g);
+int gnode_graph_info(gnode_graph_t g, int32_t* n, int64_t* nnz, int32_t* max_degree, int32_t* symmetric);
+
+/* ---- batches --------------------------------------------------------------
+ * Replaces scipy.sparse.block_diag(a) + LongTensor(idx).to(device), executed by
+ * the reference on the host at EVERY Euler step (ode_nn_ngraph_sim.py:68-71,
+ * ode_nn_ngraphs.py:65-71). Built once per distinct instance list. */
+int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_inst, gnode_batch_t* out);
+int gnode_batch_destroy(gnode_batch_t b);
+int64_t gnode_batch_rows(gnode_batch_t b);
+
+/* ---- a7: neighbour aggregation -------------------------------------------
+ * out[r,:] = sum over stored (r,c) of in[c,:]   (transpose != 0: over stored (c,r)).
+ * Replaces the gather / repeat / scatter_add_ at ode_nn_ngraph_sim.py:73,
+ * ode_nn_ngraphs.py:73. in/out: [M,H]. */
+int gnode_aggregate(gnode_batch_t b, const float* in, float* out, int transpose, void* stream);
+
+/* ---- a5-a8: one evaluation of the ODE right-hand side ----------------------
+ * Replaces ODEfunc.forward(t, y) (ode_nn_ngraph_sim.py:58-96, ode_nn_ngraphs.py:54-83).
+ * y, dy: [3,M,H] (S,I,R planes); beta,gamma: [M]; scratch: [M,H] floats. */
+int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* beta, const float* gamma,
+                       const gnode_params_t* p, float* dy, float* scratch, void* stream);
+
+/* ---- a1-a9: the whole rollout ---------------------------------------------
+ * Replaces ODEBlock.forward (ode_nn_ngraph_sim.py:148-188, ode_nn_ngraphs.py:124-152)
+ * including torchdiffeq's fixed-grid Euler loop (odeint(..., method='euler')).
+ *   x      [M, ldx] fp32, ldx >= 5: columns S0 I0 R0 beta gamma (rest ignored)
+ *   T      number of grid points (len(integration_time)); dt_host[T-1] HOST floats
+ *          dt_k = (float)(t_{k+1} - t_k)
+ *   traj   [T,3,M,H] or NULL. NULL = inference (states ping-pong in the workspace)
+ *   probs  [T,M,3]  softmax probabilities (S,I,R) of every grid state
+ *   workspace: gnode_rollout_workspace_bytes(b, traj != NULL) bytes, 256-B aligned */
+size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj);
+int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                          int32_t T, const float* dt_host, float* traj, float* probs,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a10: backward (reverse sweep over the stored trajectory) --------------
+ * Replaces torchdiffeq OdeintAdjointMethod.backward + autograd of the encoder /
+ * decoder (entered from loss.backward(), ode_nn_ngraph_sim.py:245).
+ *   grad_probs [T,M,3] = dL/dprobs;  grads_out [GNODE_GRAD_COUNT] (overwritten)
+ *   workspace: gnode_backward_workspace_bytes(b) bytes */
+size_t gnode_backward_workspace_bytes(gnode_batch_t b);
+int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                           int32_t T, const float* dt_host, const float* traj,
+                           const float* grad_probs, int32_t grad_mode, float* grads_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNODE_B200_H */
