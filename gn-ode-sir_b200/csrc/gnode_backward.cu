@@ -1,16 +1,514 @@
-// Backward reverse sweep (a10) -- placeholder until the kernels land.
+// Backward: reverse sweep over the stored trajectory (a10; 3C).
+//
+// Replaces torchdiffeq's OdeintAdjointMethod.backward (entered from loss.backward(),
+// ode_nn_ngraph_sim.py:245) plus autograd of the encoder (:151-156) and decoder (:172-187).
+//
+// With f the right-hand side (ode_nn_ngraph_sim.py:58-96) and cotangent a = (aS, aI, aR):
+//   q    = aI - aS
+//   gAI  = beta * q * S'                      gS' = beta * q * AI
+//   gI'  = A^T gAI + gamma * (aR - aI)
+//   gzS  = gS' * S'(1-S')                     gzI = gI' * I'(1-I')
+//   vS   = gzS W ; vI = gzI W ; vR = 0        (VJP wrt the state)
+//   vW   = gzS^T S + gzI^T I ; vb = sum_rows(gzS + gzI)
+// grad_mode ADJOINT  (torchdiffeq semantics, what the reference trains with):
+//   for j = T-1 .. 1:  a += D(y_j, gP_j);  a, g_theta += dt_{j-1} * VJP(y_j; a);   finally a += D(y_0, gP_0)
+// grad_mode DISCRETE (exact gradient of the Euler loop):
+//   a = D(y_{T-1}, gP_{T-1});  for j = T-2 .. 0:  (v, v_theta) = VJP(y_j; a);  a += D(y_j, gP_j) + dt_j v
+// where D(y, gP) is the decoder+softmax backward. Then the encoder backward on a_0.
+//
+// Per reverse step three launches (two grid-wide dependencies: I' before A I', gAI before A^T gAI):
+//   K1 bwd_transform_kernel : S' = sig(S_j W^T+b), I' = sig(I_j W^T+b)          -> Sp, Ip
+//   K2 bwd_row_kernel       : AI = A I' ; a += D(y_j,gP_j) (adjoint mode) ; gAI   -> AI, G, a
+//                             (discrete mode adds D in a separate row pass after K3)
+//   K3 bwd_vjp_kernel       : A^T gAI, gz*, v = gz W into a, per-CTA vW / vb
+// Parameter-gradient partial sums live in per-CTA slots (no atomics: bitwise reproducible) and are
+// folded by reduce_partials_kernel at the end.
+#include <algorithm>
+
 #include "gnode_common.cuh"
+#include "gnode_tile.cuh"
+
+namespace gnode {
+
+constexpr int ROW_THREADS = 256;                 // K2 / K4 block size (16 half-warps)
+constexpr int DEC_COUNT = 4 * H + 4 + 4 + 1;     // linear3.weight, linear3.bias, linearS2.weight, linearS2.bias
+constexpr int LIN_COUNT = H * H + H;             // odefunc.linear.weight, bias
+constexpr int ENC_COUNT = 2 * H;                 // linearS1.weight, bias
+
+struct BwdArgs {
+    GnBatchView bv;
+    const float* x; int64_t ldx;   // beta = x[:,3], gamma = x[:,4]; encoder inputs x[:,0:3]
+    const float* y;                // [3][M][H] state y_j
+    const float* gP;               // [M][3] dL/dprobs at time j (may be null: no decoder term)
+    float* a;                      // [3][M][H] adjoint (in place)
+    float* Sp; float* Ip; float* AI; float* G;   // [M][H] scratch
+    float* part;                   // per-block partial sums of this kernel family
+    float dt;
+    int only_dec;                  // 1: only a += D(y, gP)
+    gnode_params_t p;
+};
+
+// ---------------------------------------------------------------- K1
+constexpr int K1_SM_X = 0, K1_SM_O = 32768, K1_SM_W = 65536, K1_SM_B = K1_SM_W + H * H * 4, K1_SM_TOTAL = K1_SM_B + H * 4;
+
+__global__ void __launch_bounds__(NTHREADS, 2) bwd_transform_kernel(const BwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* Xs = smem + K1_SM_X;
+    unsigned char* Os = smem + K1_SM_O;
+    float* Ws = reinterpret_cast<float*>(smem + K1_SM_W);
+    float* bs = reinterpret_cast<float*>(smem + K1_SM_B);
+    const int tid = threadIdx.x;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    for (int i = tid; i < H * H / 4; i += NTHREADS)
+        reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TILE;
+#pragma unroll 1
+        for (int comp = 0; comp < 2; ++comp) {
+            load_tile(Xs, a.y + comp * plane, tile0, M, tid);
+            __syncthreads();
+            gemm_sigmoid(Xs, Ws, bs, Os, tid);
+            __syncthreads();
+            store_tile(comp == 0 ? a.Sp : a.Ip, Os, tile0, M, tid);
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- decoder backward for one row
+// Row held 4 channels per lane by a half-warp. Returns d = D(y, gP) for the lane's channels and
+// accumulates the decoder parameter gradients into per-thread registers.
+struct DecAcc {
+    float w3[16];     // [m][j]: d linear3.weight[m][4l+j]
+    float b3[4], w2[4], b2;
+};
+
+__device__ __forceinline__ void decoder_backward_row(const float4 (&c)[3], const float* gP_row, const float* W3s,
+                                                     const float* small, int l, bool valid, float4 (&d)[3],
+                                                     DecAcc& acc) {
+    float hid[12];
+    float4 w3[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        w3[m] = *reinterpret_cast<const float4*>(W3s + m * H + 4 * l);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) hid[4 * k + m] = dot4(c[k], w3[m]);
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1)
+#pragma unroll
+        for (int m = 0; m < 12; ++m) hid[m] += __shfl_xor_sync(0xffffffffu, hid[m], off);
+    const float* b3 = small; const float* w2 = small + 4; const float b2 = small[8];
+    float o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float s = b2;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { hid[4 * k + m] += b3[m]; s = fmaf(w2[m], fmaxf(hid[4 * k + m], 0.f), s); }
+        o[k] = s;
+    }
+    const float mx = fmaxf(o[0], fmaxf(o[1], o[2]));
+    float P[3] = {expf(o[0] - mx), expf(o[1] - mx), expf(o[2] - mx)};
+    const float inv = 1.0f / (P[0] + P[1] + P[2]);
+    float g[3] = {0.f, 0.f, 0.f};
+    if (valid && gP_row != nullptr) { g[0] = gP_row[0]; g[1] = gP_row[1]; g[2] = gP_row[2]; }
+    float dotgp = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { P[k] *= inv; dotgp = fmaf(g[k], P[k], dotgp); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float go = P[k] * (g[k] - dotgp);                // softmax backward
+        float4 dk = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const float act = fmaxf(hid[4 * k + m], 0.f);
+            const float gh = (hid[4 * k + m] > 0.f) ? go * w2[m] : 0.f;   // ReLU backward
+            dk.x = fmaf(gh, w3[m].x, dk.x); dk.y = fmaf(gh, w3[m].y, dk.y);
+            dk.z = fmaf(gh, w3[m].z, dk.z); dk.w = fmaf(gh, w3[m].w, dk.w);
+            acc.w3[4 * m + 0] = fmaf(gh, c[k].x, acc.w3[4 * m + 0]); acc.w3[4 * m + 1] = fmaf(gh, c[k].y, acc.w3[4 * m + 1]);
+            acc.w3[4 * m + 2] = fmaf(gh, c[k].z, acc.w3[4 * m + 2]); acc.w3[4 * m + 3] = fmaf(gh, c[k].w, acc.w3[4 * m + 3]);
+            if (l == 0) { acc.b3[m] += gh; acc.w2[m] = fmaf(go, act, acc.w2[m]); }
+        }
+        if (l == 0) acc.b2 += go;
+        d[k] = dk;
+    }
+}
+
+// ---------------------------------------------------------------- K2
+__global__ void __launch_bounds__(ROW_THREADS) bwd_row_kernel(const BwdArgs a) {
+    __shared__ float W3s[4 * H];
+    __shared__ float small[12];
+    __shared__ float red[ROW_THREADS / 16][16][17];   // [half-warp][lane][16 w3 values (+pad)]
+    __shared__ float red0[ROW_THREADS / 16][9];       // lane-0 values: b3[4], w2[4], b2
+    const int tid = threadIdx.x, lane = tid & 31, l = tid & 15, hw = tid >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    for (int i = tid; i < 4 * H; i += ROW_THREADS) W3s[i] = a.p.l3_w[i];
+    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+    if (tid == 0) small[8] = a.p.s2_b[0];
+    __syncthreads();
+
+    DecAcc acc;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc.w3[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc.b3[i] = 0.f; acc.w2[i] = 0.f; }
+    acc.b2 = 0.f;
+
+    const int hw_per_grid = gridDim.x * (ROW_THREADS / 16);
+    // warp-uniform trip count: both half-warps of a warp walk rows r and r+1
+    const int64_t n_iter = (M + hw_per_grid - 1) / hw_per_grid;
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t g = it * hw_per_grid + (int64_t)blockIdx.x * (ROW_THREADS / 16) + hw;
+        const bool valid = g < M;
+        const size_t off = (size_t)(valid ? g : 0) * H + 4 * l;
+        float4 AI = make_float4(0.f, 0.f, 0.f, 0.f);
+        float be = 0.f;
+        if (!a.only_dec) {
+            int row0 = 0, e0 = 0, deg = 0;
+            const int32_t* ci = nullptr;
+            if (valid) {
+                const GnInstance I = a.bv.inst[find_instance(a.bv, g)];
+                row0 = I.row0; ci = I.colidx;
+                const int n = (int)(g - row0);
+                e0 = I.rowptr[n];
+                deg = I.rowptr[n + 1] - e0;
+                be = a.x[(size_t)g * a.ldx + 3];
+            }
+            AI = gather_row(a.Ip, ci, e0, deg, row0, l, lane);
+        }
+        float4 c[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) c[k] = valid ? ldg4_stream(a.y + k * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        decoder_backward_row(c, (valid && a.gP) ? a.gP + (size_t)g * 3 : nullptr, W3s, small, l, valid, d, acc);
+        if (valid) {
+            float4 av[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) av[k] = ldg4(a.a + k * plane + off);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { av[k].x += d[k].x; av[k].y += d[k].y; av[k].z += d[k].z; av[k].w += d[k].w; }
+            if (!a.only_dec) {
+                const float4 sp = ldg4(a.Sp + off);
+                float4 G;
+                G.x = be * (av[1].x - av[0].x) * sp.x; G.y = be * (av[1].y - av[0].y) * sp.y;
+                G.z = be * (av[1].z - av[0].z) * sp.z; G.w = be * (av[1].w - av[0].w) * sp.w;
+                stg4(a.G + off, G);
+                stg4(a.AI + off, AI);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) stg4(a.a + k * plane + off, av[k]);
+        }
+    }
+    // block reduction in a fixed order (deterministic), then this block's slot += result
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[hw][l][i] = acc.w3[i];
+    if (l == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { red0[hw][i] = acc.b3[i]; red0[hw][4 + i] = acc.w2[i]; }
+        red0[hw][8] = acc.b2;
+    }
+    __syncthreads();
+    float* slot = a.part + (size_t)blockIdx.x * DEC_COUNT;
+    if (tid < 4 * H) {                               // entry (m, h): h = 4*lane16 + j
+        const int m = tid / H, h = tid % H;
+        float s = 0.f;
+        for (int w = 0; w < ROW_THREADS / 16; ++w) s += red[w][h >> 2][4 * m + (h & 3)];
+        slot[tid] += s;
+    }
+    if (tid < 9) {
+        float s = 0.f;
+        for (int w = 0; w < ROW_THREADS / 16; ++w) s += red0[w][tid];
+        slot[4 * H + tid] += s;
+    }
+}
+
+// ---------------------------------------------------------------- K3
+constexpr int K3_SM_GS = 0, K3_SM_GI = 32768, K3_SM_XS = 65536, K3_SM_XI = 98304, K3_SM_W = 131072,
+              K3_SM_TOTAL = K3_SM_W + H * H * 4;
+
+__global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* GS = smem + K3_SM_GS;
+    unsigned char* GI = smem + K3_SM_GI;
+    unsigned char* XS = smem + K3_SM_XS;
+    unsigned char* XI = smem + K3_SM_XI;
+    float* Ws = reinterpret_cast<float*>(smem + K3_SM_W);
+    const int tid = threadIdx.x, lane = tid & 31, l = tid & 15, hw = tid >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    for (int i = tid; i < H * H / 4; i += NTHREADS)
+        reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+
+    // weight-gradient accumulators: thread (h = tid>>3, js = tid&7) owns vW[h][8js..8js+7] (+ vb[h] if js==0)
+    const int wh = tid >> 3, wjs = tid & 7;
+    float gw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gw[i] = 0.f;
+    float gb = 0.f;
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TILE;
+        // state tiles for the weight gradient (asynchronous; waited on before the GEMM phase)
+        for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
+            const int rr = idx >> 4, c4 = idx & 15;
+            const int64_t g = tile0 + rr;
+            if (g < M) {
+                cp_async16(XS + sw_off(rr, c4), a.y + (size_t)g * H + 4 * c4);
+                cp_async16(XI + sw_off(rr, c4), a.y + plane + (size_t)g * H + 4 * c4);
+            } else {
+                sts4(XS, sw_off(rr, c4), make_float4(0.f, 0.f, 0.f, 0.f));
+                sts4(XI, sw_off(rr, c4), make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
+        // ---- row phase: A^T gAI, then the cotangents wrt the pre-activations
+        int inst = a.bv.tile_inst[tile];
+#pragma unroll 1
+        for (int it = 0; it < TILE / 32; ++it) {
+            const int rr = hw + 32 * it;
+            const int64_t g = tile0 + rr;
+            const bool valid = g < M;
+            int row0 = 0, e0 = 0, deg = 0;
+            const int32_t* ci = nullptr;
+            float be = 0.f, ga = 0.f;
+            if (valid) {
+                while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                const GnInstance I = a.bv.inst[inst];
+                row0 = I.row0; ci = I.colidx_t;
+                const int n = (int)(g - row0);
+                e0 = I.rowptr_t[n];
+                deg = I.rowptr_t[n + 1] - e0;
+                be = a.x[(size_t)g * a.ldx + 3];
+                ga = a.x[(size_t)g * a.ldx + 4];
+            }
+            const float4 gsum = gather_row(a.G, ci, e0, deg, row0, l, lane);
+            float4 gzs = make_float4(0.f, 0.f, 0.f, 0.f), gzi = gzs;
+            if (valid) {
+                const size_t off = (size_t)g * H + 4 * l;
+                const float4 aS = ldg4(a.a + off), aI = ldg4(a.a + plane + off), aR = ldg4(a.a + 2 * plane + off);
+                const float4 sp = ldg4_stream(a.Sp + off), ip = ldg4_stream(a.Ip + off), ai = ldg4_stream(a.AI + off);
+#define GN_GZ(c)                                                               \
+    {                                                                          \
+        const float q = aI.c - aS.c;                                           \
+        const float gip = gsum.c + ga * (aR.c - aI.c);                         \
+        gzi.c = gip * ip.c * (1.0f - ip.c);                                    \
+        gzs.c = be * q * ai.c * sp.c * (1.0f - sp.c);                          \
+    }
+                GN_GZ(x) GN_GZ(y) GN_GZ(z) GN_GZ(w)
+#undef GN_GZ
+            }
+            sts4(GS, sw_off(rr, l), gzs);
+            sts4(GI, sw_off(rr, l), gzi);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // ---- v = gz W into the adjoint: warps 0-7 -> aS, warps 8-15 -> aI (aR: vR = 0)
+        {
+            const int t = tid & 255;
+            const int comp = tid >> 8;
+            float v0[16], v1[16];
+            gemm_gw(comp == 0 ? GS : GI, Ws, t, v0, v1);
+            const int r0 = t & 63, q = t >> 6;
+            float* ap = a.a + comp * plane;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int64_t g = tile0 + r0 + 64 * half;
+                if (g < M) {
+                    float* row = ap + (size_t)g * H + 16 * q;
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj += 4) {
+                        float4 cur = ldg4(row + jj);
+                        const float* v = half == 0 ? v0 : v1;
+                        cur.x = fmaf(a.dt, v[jj + 0], cur.x); cur.y = fmaf(a.dt, v[jj + 1], cur.y);
+                        cur.z = fmaf(a.dt, v[jj + 2], cur.z); cur.w = fmaf(a.dt, v[jj + 3], cur.w);
+                        stg4(row + jj, cur);
+                    }
+                }
+            }
+        }
+        // ---- vW[h][j] += sum_r gzS[r][h] S[r][j] + gzI[r][h] I[r][j] ; vb[h] += sum_r gzS + gzI
+#pragma unroll 4
+        for (int r = 0; r < TILE; ++r) {
+            const float gs = *reinterpret_cast<const float*>(GS + sw_off(r, wh >> 2) + 4 * (wh & 3));
+            const float gi = *reinterpret_cast<const float*>(GI + sw_off(r, wh >> 2) + 4 * (wh & 3));
+            const float4 s0 = lds4(XS, sw_off(r, 2 * wjs)), s1 = lds4(XS, sw_off(r, 2 * wjs + 1));
+            const float4 i0 = lds4(XI, sw_off(r, 2 * wjs)), i1 = lds4(XI, sw_off(r, 2 * wjs + 1));
+            gw[0] = fmaf(gs, s0.x, gw[0]); gw[1] = fmaf(gs, s0.y, gw[1]); gw[2] = fmaf(gs, s0.z, gw[2]); gw[3] = fmaf(gs, s0.w, gw[3]);
+            gw[4] = fmaf(gs, s1.x, gw[4]); gw[5] = fmaf(gs, s1.y, gw[5]); gw[6] = fmaf(gs, s1.z, gw[6]); gw[7] = fmaf(gs, s1.w, gw[7]);
+            gw[0] = fmaf(gi, i0.x, gw[0]); gw[1] = fmaf(gi, i0.y, gw[1]); gw[2] = fmaf(gi, i0.z, gw[2]); gw[3] = fmaf(gi, i0.w, gw[3]);
+            gw[4] = fmaf(gi, i1.x, gw[4]); gw[5] = fmaf(gi, i1.y, gw[5]); gw[6] = fmaf(gi, i1.z, gw[6]); gw[7] = fmaf(gi, i1.w, gw[7]);
+            gb += gs + gi;
+        }
+        __syncthreads();
+    }
+    float* slot = a.part + (size_t)blockIdx.x * LIN_COUNT;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) slot[wh * H + 8 * wjs + i] += a.dt * gw[i];
+    if (wjs == 0) slot[H * H + wh] += a.dt * gb;
+}
+
+// ---------------------------------------------------------------- K4: encoder backward
+// y0 = relu(c * w1 + b1): d w1[h] = sum a0[h] [y0>0] c ; d b1[h] = sum a0[h] [y0>0]   (c in {S0,I0,R0})
+__global__ void __launch_bounds__(ROW_THREADS) bwd_encoder_kernel(const BwdArgs a) {
+    __shared__ float red[ROW_THREADS / 16][16][9];
+    const int tid = threadIdx.x, l = tid & 15, hw = tid >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    float gw[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t g = (int64_t)blockIdx.x * (ROW_THREADS / 16) + hw; g < M; g += (int64_t)gridDim.x * (ROW_THREADS / 16)) {
+        const size_t off = (size_t)g * H + 4 * l;
+        const float* xr = a.x + (size_t)g * a.ldx;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float c = xr[k];
+            const float4 y0 = ldg4_stream(a.y + k * plane + off);
+            const float4 av = ldg4_stream(a.a + k * plane + off);
+            const float m0 = y0.x > 0.f ? av.x : 0.f, m1 = y0.y > 0.f ? av.y : 0.f;
+            const float m2 = y0.z > 0.f ? av.z : 0.f, m3 = y0.w > 0.f ? av.w : 0.f;
+            gw[0] = fmaf(m0, c, gw[0]); gw[1] = fmaf(m1, c, gw[1]); gw[2] = fmaf(m2, c, gw[2]); gw[3] = fmaf(m3, c, gw[3]);
+            gb[0] += m0; gb[1] += m1; gb[2] += m2; gb[3] += m3;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { red[hw][l][i] = gw[i]; red[hw][l][4 + i] = gb[i]; }
+    __syncthreads();
+    float* slot = a.part + (size_t)blockIdx.x * ENC_COUNT;
+    if (tid < 2 * H) {
+        const int which = tid / H, h = tid % H;
+        float s = 0.f;
+        for (int w = 0; w < ROW_THREADS / 16; ++w) s += red[w][h >> 2][4 * which + (h & 3)];
+        slot[tid] = s;
+    }
+}
+
+// out[i] = sum over slots (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_slots, int count, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int k = 0; k < n_slots; ++k) s += part[(size_t)k * count + i];
+    out[i] = s;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct BwdPlan {
+    int grid_row, grid_tile1, grid_tile3;
+    size_t off_a, off_sp, off_ip, off_ai, off_g, off_pdec, off_plin, off_penc, total;
+};
+
+static BwdPlan plan_backward(const gnode_batch* b) {
+    BwdPlan p;
+    const size_t M = (size_t)b->M;
+    const int hw_per_block = ROW_THREADS / 16;
+    p.grid_row = (int)std::min<int64_t>((b->M + hw_per_block - 1) / hw_per_block, (int64_t)b->sm_count * 8);
+    p.grid_tile1 = std::min(b->n_tiles, 2 * b->sm_count);
+    p.grid_tile3 = std::min(b->n_tiles, b->sm_count);
+    size_t o = 0;
+    p.off_a = o;  o += align_up(3 * M * H * sizeof(float), 256);
+    p.off_sp = o; o += align_up(M * H * sizeof(float), 256);
+    p.off_ip = o; o += align_up(M * H * sizeof(float), 256);
+    p.off_ai = o; o += align_up(M * H * sizeof(float), 256);
+    p.off_g = o;  o += align_up(M * H * sizeof(float), 256);
+    p.off_pdec = o; o += align_up((size_t)p.grid_row * DEC_COUNT * sizeof(float), 256);
+    p.off_plin = o; o += align_up((size_t)p.grid_tile3 * LIN_COUNT * sizeof(float), 256);
+    p.off_penc = o; o += align_up((size_t)p.grid_row * ENC_COUNT * sizeof(float), 256);
+    p.total = o;
+    return p;
+}
+
+}  // namespace gnode
 
 using namespace gnode;
 
 extern "C" size_t gnode_backward_workspace_bytes(gnode_batch_t b) {
-    (void)b;
-    return 256;
+    if (!b) return 0;
+    return plan_backward(b).total;
 }
 
-extern "C" int gnode_rollout_backward(gnode_batch_t, const float*, int64_t, const gnode_params_t*, int32_t,
-                                      const float*, const float*, const float*, int32_t, float*, void*, size_t,
-                                      void*) {
-    set_error("gnode_rollout_backward: not implemented yet");
-    return GNODE_ERR_UNSUPPORTED;
+extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                      int32_t T, const float* dt_host, const float* traj, const float* grad_probs,
+                                      int32_t grad_mode, float* grads_out, void* workspace, size_t workspace_bytes,
+                                      void* stream_) {
+    if (!b || !x || !p || !traj || !grad_probs || !grads_out || !workspace || T < 1 || ldx < 5 ||
+        (T > 1 && !dt_host) || (grad_mode != GNODE_GRAD_ADJOINT && grad_mode != GNODE_GRAD_DISCRETE)) {
+        set_error("gnode_rollout_backward: bad arguments (T=%d ldx=%lld grad_mode=%d)", T, (long long)ldx, grad_mode);
+        return GNODE_ERR_ARG;
+    }
+    const BwdPlan pl = plan_backward(b);
+    if (workspace_bytes < pl.total) {
+        set_error("gnode_rollout_backward: workspace too small (%zu < %zu)", workspace_bytes, pl.total);
+        return GNODE_ERR_ARG;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(bwd_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SM_TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(bwd_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SM_TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const size_t M = (size_t)b->M;
+    unsigned char* ws = (unsigned char*)workspace;
+    BwdArgs a;
+    a.bv = gn_view(b);
+    a.x = x; a.ldx = ldx; a.p = *p;
+    a.a = (float*)(ws + pl.off_a);
+    a.Sp = (float*)(ws + pl.off_sp); a.Ip = (float*)(ws + pl.off_ip);
+    a.AI = (float*)(ws + pl.off_ai); a.G = (float*)(ws + pl.off_g);
+    float* pdec = (float*)(ws + pl.off_pdec);
+    float* plin = (float*)(ws + pl.off_plin);
+    float* penc = (float*)(ws + pl.off_penc);
+    // adjoint and partial-sum slots start at zero
+    GN_CUDA(cudaMemsetAsync(ws + pl.off_a, 0, 3 * M * H * sizeof(float), stream));
+    GN_CUDA(cudaMemsetAsync(ws + pl.off_pdec, 0, pl.off_penc - pl.off_pdec, stream));
+
+    auto state = [&](int j) { return traj + (size_t)j * 3 * M * H; };
+    auto gp = [&](int j) { return grad_probs + (size_t)j * M * 3; };
+    auto dec_only = [&](int j) -> int {
+        a.y = state(j); a.gP = gp(j); a.part = pdec; a.only_dec = 1; a.dt = 0.f;
+        bwd_row_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+        GN_LAUNCH_CHECK();
+        return GNODE_OK;
+    };
+    auto vjp_step = [&](int j, float dt, bool with_decoder) -> int {
+        a.y = state(j); a.gP = with_decoder ? gp(j) : nullptr; a.dt = dt; a.only_dec = 0;
+        a.part = nullptr;
+        bwd_transform_kernel<<<pl.grid_tile1, NTHREADS, K1_SM_TOTAL, stream>>>(a);
+        GN_LAUNCH_CHECK();
+        a.part = pdec;
+        bwd_row_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+        GN_LAUNCH_CHECK();
+        a.part = plin;
+        bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
+        GN_LAUNCH_CHECK();
+        return GNODE_OK;
+    };
+    int rc;
+    if (grad_mode == GNODE_GRAD_ADJOINT) {
+        for (int j = T - 1; j >= 1; --j)
+            if ((rc = vjp_step(j, dt_host[j - 1], true))) return rc;
+        if ((rc = dec_only(0))) return rc;
+    } else {
+        if ((rc = dec_only(T - 1))) return rc;
+        for (int j = T - 2; j >= 0; --j) {       // D(y_j) must not enter the cotangent of the VJP at y_j
+            if ((rc = vjp_step(j, dt_host[j], false))) return rc;
+            if ((rc = dec_only(j))) return rc;
+        }
+    }
+    a.y = state(0); a.part = penc;
+    bwd_encoder_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    // fold the per-block slots into the flat gradient vector (layout of include/gnode_b200.h)
+    reduce_partials_kernel<<<(LIN_COUNT + 255) / 256, 256, 0, stream>>>(plin, pl.grid_tile3, LIN_COUNT,
+                                                                        grads_out + GNODE_GRAD_OFF_LIN_W);
+    GN_LAUNCH_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(penc, pl.grid_row, ENC_COUNT, grads_out + GNODE_GRAD_OFF_S1_W);
+    GN_LAUNCH_CHECK();
+    reduce_partials_kernel<<<(DEC_COUNT + 255) / 256, 256, 0, stream>>>(pdec, pl.grid_row, DEC_COUNT,
+                                                                        grads_out + GNODE_GRAD_OFF_L3_W);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
 }

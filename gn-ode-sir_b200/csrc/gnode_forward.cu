@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "gnode_common.cuh"
+#include "gnode_tile.cuh"
 
 namespace gnode {
 
@@ -45,65 +46,6 @@ constexpr int SM_W1 = SM_W3 + 4 * H * 4;       // linearS1.weight [64]
 constexpr int SM_B1 = SM_W1 + H * 4;           // linearS1.bias [64]
 constexpr int SM_SMALL = SM_B1 + H * 4;        // b3[4], w2[4], b2[1]
 constexpr int SM_TOTAL = SM_SMALL + 64;
-
-// Z = X W^T (X: swizzled 128x64 tile, W: [h][k]) ; dst = sigmoid(Z + b), swizzled.
-// 256 threads: thread (r0 = tid&63, q = tid>>6) owns rows r0, r0+64 x columns [16q,16q+16).
-__device__ __forceinline__ void gemm_sigmoid(const unsigned char* Xs, const float* Ws, const float* bs,
-                                             unsigned char* dst, int tid) {
-    if (tid >= 256) return;
-    const int r0 = tid & 63, q = tid >> 6;
-    float a0[16], a1[16];
-#pragma unroll
-    for (int h = 0; h < 16; ++h) { a0[h] = 0.f; a1[h] = 0.f; }
-    const float* wq = Ws + (16 * q) * H;
-#pragma unroll 2
-    for (int c4 = 0; c4 < CHUNKS; ++c4) {
-        const float4 xa = lds4(Xs, sw_off(r0, c4));
-        const float4 xb = lds4(Xs, sw_off(r0 + 64, c4));
-#pragma unroll
-        for (int h = 0; h < 16; ++h) {
-            const float4 w = *reinterpret_cast<const float4*>(wq + h * H + 4 * c4);
-            a0[h] = fmaf(xa.x, w.x, a0[h]); a0[h] = fmaf(xa.y, w.y, a0[h]);
-            a0[h] = fmaf(xa.z, w.z, a0[h]); a0[h] = fmaf(xa.w, w.w, a0[h]);
-            a1[h] = fmaf(xb.x, w.x, a1[h]); a1[h] = fmaf(xb.y, w.y, a1[h]);
-            a1[h] = fmaf(xb.z, w.z, a1[h]); a1[h] = fmaf(xb.w, w.w, a1[h]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * q + 4 * j);
-        float4 o0, o1;
-        o0.x = sigmoidf_acc(a0[4 * j + 0] + bb.x); o0.y = sigmoidf_acc(a0[4 * j + 1] + bb.y);
-        o0.z = sigmoidf_acc(a0[4 * j + 2] + bb.z); o0.w = sigmoidf_acc(a0[4 * j + 3] + bb.w);
-        o1.x = sigmoidf_acc(a1[4 * j + 0] + bb.x); o1.y = sigmoidf_acc(a1[4 * j + 1] + bb.y);
-        o1.z = sigmoidf_acc(a1[4 * j + 2] + bb.z); o1.w = sigmoidf_acc(a1[4 * j + 3] + bb.w);
-        sts4(dst, sw_off(r0, 4 * q + j), o0);
-        sts4(dst, sw_off(r0 + 64, 4 * q + j), o1);
-    }
-}
-
-// coalesced HBM rows -> swizzled tile (rows past M are zero-filled)
-__device__ __forceinline__ void load_tile(unsigned char* dst, const float* src, int64_t tile0, int M, int tid) {
-    for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
-        const int rr = idx >> 4, c4 = idx & 15;
-        const int64_t g = tile0 + rr;
-        if (g < M) cp_async16(dst + sw_off(rr, c4), src + (size_t)g * H + 4 * c4);
-        else sts4(dst, sw_off(rr, c4), make_float4(0.f, 0.f, 0.f, 0.f));
-    }
-    cp_async_wait_all();
-}
-
-__device__ __forceinline__ void store_tile(float* dst, const unsigned char* src, int64_t tile0, int M, int tid) {
-    for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
-        const int rr = idx >> 4, c4 = idx & 15;
-        const int64_t g = tile0 + rr;
-        if (g < M) stg4(dst + (size_t)g * H + 4 * c4, lds4(src, sw_off(rr, c4)));
-    }
-}
-
-__device__ __forceinline__ float dot4(float4 a, float4 b) {
-    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
-}
 
 // decoder + softmax of one row held 4 channels per lane by a half-warp
 // (linear3 -> ReLU -> linearS2 -> softmax over {S,I,R}; ode_nn_ngraph_sim.py:172-187)
@@ -197,25 +139,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
                     e0 = I.rowptr[n];
                     deg = I.rowptr[n + 1] - e0;
                 }
-                const int degmax = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
-                // ---- aggregation: sequential ascending-column sum, 8 rows in flight per lane
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int eb = 0; eb < degmax; eb += 16) {
-                    const int mine = (eb + l < deg) ? ci[e0 + eb + l] + row0 : -1;
-#pragma unroll
-                    for (int jb = 0; jb < 16; jb += 8) {
-                        if (eb + jb < degmax) {
-                            float4 v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int c = __shfl_sync(0xffffffffu, mine, (lane & 16) + jb + j);
-                                v[j] = (c >= 0) ? ldg4(a.ip_in + (size_t)c * H + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-                        }
-                    }
-                }
+                // ---- aggregation: sequential ascending-column sum (ode_nn_ngraph_sim.py:73)
+                const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
                 // ---- SIR derivative + Euler update (explicit _rn ops: no FMA contraction, the
                 //      reference rounds after every ATen op)
                 float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;

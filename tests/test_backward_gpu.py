@@ -1,0 +1,121 @@
+"""GPU parity of the reverse sweep (a10) against the reference's own gradients
+(tests/golden, produced by loss.backward() through the reference classes with the restated
+torchdiffeq adjoint) and against the oracle on fresh seeds.
+Tolerance: fp32 gradients are long reductions (over T*M*H terms) whose summation order differs
+between implementations; 2e-4 * max|grad| per tensor (the oracle's own fp32-vs-reference noise is
+~2e-6, tests/test_oracle_golden.py), and 1e-3 against the float64 gradients."""
+import pytest
+import torch
+
+from _util import GOLDEN_CASES, Golden
+from oracle import gnode_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_CASES = [c for c in GOLDEN_CASES if "fbsocial" not in c]
+
+
+@pytest.fixture(scope="module")
+def gn():
+    import gn_ode_sir_b200 as g
+    g.build_library()
+    return g
+
+
+def build_block(gn, g, mode):
+    if g.variant == "sim":
+        of = gn.ode_sim.ODEfunc(g.adjs[0], 0.2, 0.1, g.H, DEV)
+        blk = gn.ode_sim.ODEBlock(g.maxTime, g.deltaT, g.adjs[0].shape[0], [0, 1], g.H, of, DEV)
+    else:
+        of = gn.ode_ngraphs.ODEfunc(g.adjs, g.H, DEV)
+        blk = gn.ode_ngraphs.ODEBlock(g.maxTime, g.deltaT, g.H, of, DEV)
+    blk.load_state_dict(g.params)
+    blk.to(DEV)
+    blk.grad_mode = mode
+    return blk
+
+
+def cuda_grads(gn, g, mode):
+    blk = build_block(gn, g, mode)
+    blk.train()
+    S, I, R = blk(g.x_as_model_input().to(DEV))
+    probs = torch.cat((S, I, R), -1)
+    (probs * g.weight().to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    return blk, probs.detach().cpu()
+
+
+@pytest.mark.parametrize("mode", ["adjoint", "discrete"])
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_gradients_match_reference(gn, name, mode):
+    g = Golden(name)
+    blk, probs = cuda_grads(gn, g, mode)
+    assert (probs - g.probs32).abs().max().item() < 1e-5       # training-mode forward (trajectory stored)
+    got = {k: p.grad.detach().cpu() for k, p in blk.named_parameters() if p.grad is not None}
+    for k in orc.GRAD_KEYS:
+        ref32, ref64 = g.grads[("g32", mode)][k], g.grads[("g64", mode)][k]
+        scale = ref64.abs().max().item() + 1e-30
+        e32 = (got[k] - ref32).abs().max().item() / scale
+        e64 = (got[k].double() - ref64).abs().max().item() / scale
+        assert e32 < 2e-4 and e64 < 1e-3, (k, e32, e64)
+    if mode == "adjoint":
+        # unused LayerNorm of ODEfunc: zero gradients (not None), like torchdiffeq's adjoint params
+        assert float(got["odefunc.ln.weight"].abs().max()) == 0.0
+        assert float(got["odefunc.ln.bias"].abs().max()) == 0.0
+    assert blk.ln.weight.grad is None
+
+
+def test_backward_is_deterministic(gn):
+    g = Golden("ng_mixed_b5")
+    b1, _ = cuda_grads(gn, g, "adjoint")
+    b2, _ = cuda_grads(gn, g, "adjoint")
+    for (k, p1), (_, p2) in zip(b1.named_parameters(), b2.named_parameters()):
+        if p1.grad is not None:
+            assert torch.equal(p1.grad, p2.grad), k
+
+
+def test_gradients_fresh_seed_uneven_tiles(gn):
+    """M = 7*62 = 434 rows (not a tile multiple), non-default grid, both modes vs the oracle in fp64."""
+    g = Golden("sim_dolphins_b4")
+    A, N, B = g.adjs[0], g.adjs[0].shape[0], 7
+    params = orc.default_params(64, seed=77)
+    x = torch.cat([orc.synthetic_trial(N, 64, 300 + b) for b in range(B)])
+    t = orc.time_grid(6, 0.25)
+    w = torch.randn(len(t), B * N, 3, generator=torch.Generator().manual_seed(8))
+    coo = orc.batch_coo([A], [0] * B)
+    for mode in ("adjoint", "discrete"):
+        torch.set_default_dtype(torch.float64)
+        try:
+            _, want = orc.loss_and_grads(x.double(), {k: v.double() for k, v in params.items()}, coo, t, w.double(), mode)
+        finally:
+            torch.set_default_dtype(torch.float32)
+        of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, DEV)
+        blk = gn.ode_sim.ODEBlock(6, 0.25, N, [0, 1], 64, of, DEV)
+        blk.load_state_dict(params)
+        blk.to(DEV)
+        blk.grad_mode = mode
+        S, I, R = blk(x.view(B, N, -1).to(DEV))
+        (torch.cat((S, I, R), -1) * w.to(DEV)).sum().backward()
+        for k in orc.GRAD_KEYS:
+            got = dict(blk.named_parameters())[k].grad.cpu().double()
+            scale = want[k].abs().max().item() + 1e-30
+            assert (got - want[k]).abs().max().item() / scale < 1e-3, (mode, k)
+
+
+def test_training_step_reduces_loss(gn):
+    """Three Adam steps on karate through the drop-in module (what train() does,
+    ode_nn_ngraph_sim.py:217-246) lower the L1 loss on a fixed target."""
+    g = Golden("sim_karate_b8")
+    blk = build_block(gn, g, "adjoint")
+    opt = torch.optim.Adam(blk.parameters(), lr=1e-2)
+    x = g.x_as_model_input().to(DEV)
+    target = g.probs64.float().to(DEV).roll(1, dims=-1)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        S, I, R = blk(x)
+        loss = torch.nn.functional.l1_loss(torch.cat((S, I, R), -1), target)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
