@@ -31,6 +31,8 @@ SIGNATURES = {
     "gnode_last_error": (ctypes.c_char_p, []),
     "gnode_version": (c_int, []),
     "gnode_launch_count": (c_int64, []),
+    "gnode_set_variant": (c_int, [c_int]),
+    "gnode_get_variant": (c_int, []),
     "gnode_graph_create": (c_int, [c_int32, c_int64, c_int32_p, c_int32_p, ctypes.POINTER(c_void_p)]),
     "gnode_graph_destroy": (c_int, [c_void_p]),
     "gnode_graph_info": (c_int, [c_void_p, c_int32_p, ctypes.POINTER(c_int64), c_int32_p, c_int32_p]),

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) bwd_transform_kernel(const BwdArg
         for (int comp = 0; comp < 2; ++comp) {
             load_tile(Xs, a.y + comp * plane, tile0, M, tid);
             __syncthreads();
-            gemm_sigmoid(Xs, Ws, bs, Os, tid);
+            gemm_sigmoid<false>(Xs, Ws, bs, Os, tid);
             __syncthreads();
             store_tile(comp == 0 ? a.Sp : a.Ip, Os, tile0, M, tid);
             __syncthreads();

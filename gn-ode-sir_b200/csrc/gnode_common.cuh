@@ -52,6 +52,7 @@ struct gnode_graph {
     int32_t* d_colidx = nullptr;    // [nnz]
     int32_t* d_rowptr_t = nullptr;  // transpose (aliases the above when symmetric)
     int32_t* d_colidx_t = nullptr;
+    std::vector<int32_t> h_rowptr;  // host copy (tile cost model at batch creation)
     int device = 0;
 };
 
@@ -72,6 +73,7 @@ struct gnode_batch {
     int64_t nnz_total = 0;
     GnInstance* d_inst = nullptr;    // [n_inst]
     int32_t* d_tile_inst = nullptr;  // [n_tiles] instance that owns the first row of each tile
+    int32_t* d_tile_order = nullptr; // [n_tiles] processing order: hub-heavy tiles first, then row-major
     int device = 0;
     int sm_count = 0;
 };
@@ -80,6 +82,7 @@ struct gnode_batch {
 struct GnBatchView {
     const GnInstance* inst;
     const int32_t* tile_inst;
+    const int32_t* tile_order;
     int32_t n_inst;
     int32_t n_tiles;
     int32_t M;
@@ -89,6 +92,7 @@ inline GnBatchView gn_view(const gnode_batch* b) {
     GnBatchView v;
     v.inst = b->d_inst;
     v.tile_inst = b->d_tile_inst;
+    v.tile_order = b->d_tile_order;
     v.n_inst = b->n_inst;
     v.n_tiles = b->n_tiles;
     v.M = (int32_t)b->M;
@@ -128,12 +132,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // sigmoid(z) = 1 / (1 + exp(-z))   (nn.Sigmoid, ode_nn_ngraph_sim.py:63)
-__device__ __forceinline__ float sigmoidf_acc(float z) {
-#ifdef GNODE_FAST_SIGMOID
-    return __fdividef(1.0f, 1.0f + __expf(-z));
-#else
-    return 1.0f / (1.0f + expf(-z));
-#endif
+//   FAST = false: expf + IEEE division (about 1.5 ulp)
+//   FAST = true : ex2.approx + rcp.approx (2 MUFU ops; about 4 ulp)
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_t(float z) {
+    if (FAST) {
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        return r;
+    } else {
+        return 1.0f / (1.0f + expf(-z));
+    }
 }
 
 }  // namespace gnode

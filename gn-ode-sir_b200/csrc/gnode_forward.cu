@@ -13,9 +13,15 @@
 // grid-wide dependency (all of I'_k before any aggregation) is the launch boundary.
 // The reference's R' = sigmoid(linear(R)) is never used (:66 vs :75-77) and is skipped.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gnode_common.cuh"
 #include "gnode_tile.cuh"
+#include "gnode_umma.cuh"
+
+#ifndef GNODE_DEFAULT_VARIANT
+#define GNODE_DEFAULT_VARIANT 0
+#endif
 
 namespace gnode {
 
@@ -33,19 +39,25 @@ struct StepArgs {
     int64_t ldx;
     float* probs;         // [M][3] slice of the produced state, or null
     float dt;
+    int* counter;         // dynamic tile scheduler (one zeroed int per launch) or null = static striding
     gnode_params_t p;
 };
 
-// shared-memory carve-up (bytes)
+// shared-memory carve-up (bytes from a 1024-B aligned base; operand tiles need 1024-B alignment)
 constexpr int SM_X = 0;                        // 32 KB  operand tile (S_k, then I_{k+1})
-constexpr int SM_SP = 32768;                   // 32 KB  S' tile, then I'_{k+1} staging
-constexpr int SM_W = 65536;                    // 16 KB  W [h][k] row-major
-constexpr int SM_B = SM_W + H * H * 4;         // bias [64]
+constexpr int SM_SP = 32768;                   // 32 KB  Xlo scratch / S' tile / I'_{k+1} staging
+constexpr int SM_W = 65536;                    // 16 KB  FFMA: W [h][k] row-major; tensor path: Whi operand
+constexpr int SM_WLO = SM_W + H * H * 4;       // 16 KB  tensor path: Wlo operand
+constexpr int SM_B = SM_WLO + H * H * 4;       // bias [64]
 constexpr int SM_W3 = SM_B + H * 4;            // linear3.weight [4][64]
 constexpr int SM_W1 = SM_W3 + 4 * H * 4;       // linearS1.weight [64]
 constexpr int SM_B1 = SM_W1 + H * 4;           // linearS1.bias [64]
 constexpr int SM_SMALL = SM_B1 + H * 4;        // b3[4], w2[4], b2[1]
-constexpr int SM_TOTAL = SM_SMALL + 64;
+constexpr int SM_MBAR = SM_SMALL + 64;         // mbarrier (8 B) + TMEM base slot (4 B)
+constexpr int SM_TOTAL = SM_MBAR + 16 + 1024;  // + slack for the manual 1024-B alignment
+
+// kernel variants: bit 0 = tcgen05 3xTF32 transform (else FFMA), bit 1 = MUFU sigmoid (else expf + IEEE div)
+constexpr int VAR_TC = 1, VAR_FASTSIG = 2;
 
 // decoder + softmax of one row held 4 channels per lane by a half-warp
 // (linear3 -> ReLU -> linearS2 -> softmax over {S,I,R}; ode_nn_ngraph_sim.py:172-187)
@@ -78,9 +90,12 @@ __device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const f
     }
 }
 
-template <int MODE>
+template <int MODE, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr bool TC = (VAR & VAR_TC) != 0;
+    constexpr bool FAST = (VAR & VAR_FASTSIG) != 0;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* Xs = smem + SM_X;
     unsigned char* SPs = smem + SM_SP;
     float* Ws = reinterpret_cast<float*>(smem + SM_W);
@@ -89,6 +104,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
     float* w1s = reinterpret_cast<float*>(smem + SM_W1);
     float* b1s = reinterpret_cast<float*>(smem + SM_B1);
     float* small = reinterpret_cast<float*>(smem + SM_SMALL);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SM_MBAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + SM_MBAR + 8);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -98,8 +115,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
     const size_t plane = (size_t)M * H;
 
     // parameters -> shared memory (once per CTA; the CTA is persistent over its tiles)
-    for (int i = tid; i < H * H / 4; i += NTHREADS)
-        reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+    umma::Ctx cx;
+    if (TC) {
+        umma::prepare_weights(a.p.lin_w, smem + SM_W, smem + SM_WLO, tid, NTHREADS);
+        if (tid < 32) umma::tmem_alloc(tslot, umma::TMEM_COLS);          // warp 0 owns alloc / dealloc
+        if (tid == 0) umma::mbar_init(mbar, 1);
+        umma::fence_before_sync();
+    } else {
+        for (int i = tid; i < H * H / 4; i += NTHREADS)
+            reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+    }
     if (tid < H) bs[tid] = a.p.lin_b[tid];
     if (MODE == MODE_ENCODE && tid < H) { w1s[tid] = a.p.s1_w[tid]; b1s[tid] = a.p.s1_b[tid]; }
     if (MODE == MODE_ENCODE || MODE == MODE_STEP) {     // decoder weights (RHS / IP callers pass none)
@@ -108,14 +133,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
         if (tid == 0) small[8] = a.p.s2_b[0];
     }
     __syncthreads();
+    if (TC) {
+        umma::fence_after_sync();
+        cx.tmem = *tslot;
+        cx.bar = mbar;
+        cx.phase = 0;
+        cx.whi = umma::smem_u32(smem + SM_W);
+        cx.wlo = umma::smem_u32(smem + SM_WLO);
+    }
 
-    for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
+    int* tile_slot = reinterpret_cast<int*>(smem + SM_MBAR + 12);
+    for (int seq = blockIdx.x;; seq += gridDim.x) {
+        if (a.counter != nullptr) {               // dynamic: next entry of the hub-first processing order
+            if (tid == 0) *tile_slot = atomicAdd(a.counter, 1);
+            __syncthreads();
+            seq = *tile_slot;
+        }
+        if (seq >= a.bv.n_tiles) break;
+        const int tile = a.bv.tile_order[seq];
         const int64_t tile0 = (int64_t)tile * TILE;
 
         if (MODE == MODE_STEP || MODE == MODE_RHS) {
             load_tile(Xs, a.y_in, tile0, M, tid);                 // S_k
             __syncthreads();
-            gemm_sigmoid(Xs, Ws, bs, SPs, tid);                   // S'
+            if (TC) umma::gemm_sigmoid_tc<FAST>(cx, Xs, SPs, bs, tid);   // S'
+            else gemm_sigmoid<FAST>(Xs, Ws, bs, SPs, tid);
             __syncthreads();
         } else if (MODE == MODE_IP) {
             load_tile(Xs, a.y_in + plane, tile0, M, tid);         // I
@@ -208,25 +250,52 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
         }
 
         if (MODE != MODE_RHS) {
-            gemm_sigmoid(Xs, Ws, bs, SPs, tid);                   // I'_{k+1}
+            if (TC) umma::gemm_sigmoid_tc<FAST>(cx, Xs, SPs, bs, tid);   // I'_{k+1}
+            else gemm_sigmoid<FAST>(Xs, Ws, bs, SPs, tid);
             __syncthreads();
             store_tile(a.ip_out, SPs, tile0, M, tid);
             __syncthreads();
         }
     }
+    if (TC) {
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid < 32) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
+    }
+}
+
+// 0 = FFMA + accurate sigmoid ... 3 = tcgen05 + MUFU sigmoid; chosen by gnode_set_variant() / GNODE_VARIANT
+static int g_variant = -1;
+
+static int current_variant() {
+    if (g_variant < 0) {
+        const char* e = getenv("GNODE_VARIANT");
+        g_variant = e ? (atoi(e) & 3) : GNODE_DEFAULT_VARIANT;
+    }
+    return g_variant;
+}
+
+template <int MODE, int VAR>
+static int launch_step_v(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(step_kernel<MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const int grid = std::min(b->n_tiles, 2 * b->sm_count);
+    step_kernel<MODE, VAR><<<grid, NTHREADS, SM_TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
 }
 
 template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        GN_CUDA(cudaFuncSetAttribute(step_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        configured = true;
+    switch (current_variant()) {
+        case 0: return launch_step_v<MODE, 0>(b, a, stream);
+        case 1: return launch_step_v<MODE, 1>(b, a, stream);
+        case 2: return launch_step_v<MODE, 2>(b, a, stream);
+        default: return launch_step_v<MODE, 3>(b, a, stream);
     }
-    const int grid = std::min(b->n_tiles, 2 * b->sm_count);
-    step_kernel<MODE><<<grid, NTHREADS, SM_TOTAL, stream>>>(a);
-    GN_LAUNCH_CHECK();
-    return GNODE_OK;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -235,10 +304,18 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 using namespace gnode;
 
+extern "C" int gnode_set_variant(int variant) {
+    if (variant < 0 || variant > 3) { set_error("gnode_set_variant: variant must be 0..3"); return GNODE_ERR_ARG; }
+    g_variant = variant;
+    return GNODE_OK;
+}
+extern "C" int gnode_get_variant(void) { return current_variant(); }
+
 extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) {
     if (!b) return 0;
     const size_t M = (size_t)b->M;
     size_t bytes = 2 * align_up(M * sizeof(float), 256);          // beta, gamma
+    bytes += 4096;                                                // tile-scheduler counters (one int per launch)
     bytes += 2 * align_up(M * H * sizeof(float), 256);            // I' ping-pong
     if (!with_traj) bytes += 2 * align_up(3 * M * H * sizeof(float), 256);  // state ping-pong
     return bytes;
@@ -261,6 +338,8 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     unsigned char* ws = (unsigned char*)workspace;
     float* beta = (float*)ws;  ws += align_up(M * sizeof(float), 256);
     float* gamma = (float*)ws; ws += align_up(M * sizeof(float), 256);
+    int* counters = (int*)ws;  ws += 4096;
+    GN_CUDA(cudaMemsetAsync(counters, 0, 4096, stream));
     float* ip[2];
     ip[0] = (float*)ws; ws += align_up(M * H * sizeof(float), 256);
     ip[1] = (float*)ws; ws += align_up(M * H * sizeof(float), 256);
@@ -279,6 +358,7 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     a.y_in = nullptr; a.ip_in = nullptr;
     a.y_out = state(0); a.ip_out = ip[0];
     a.probs = probs; a.dt = 0.f;
+    a.counter = counters;
     int rc = launch_step<MODE_ENCODE>(b, a, stream);
     if (rc) return rc;
     for (int k = 0; k + 1 < T; ++k) {
@@ -286,6 +366,7 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
         a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
         a.probs = probs + (size_t)(k + 1) * M * 3;
         a.dt = dt_host[k];
+        a.counter = (k + 1 < 1024) ? counters + (k + 1) : nullptr;
         rc = launch_step<MODE_STEP>(b, a, stream);
         if (rc) return rc;
     }
@@ -303,7 +384,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f; a.counter = nullptr;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;

@@ -101,6 +101,7 @@ extern "C" int gnode_graph_create(int32_t n, int64_t nnz, const int32_t* rowptr,
 
     gnode_graph* g = new gnode_graph();
     g->n = n; g->nnz = nnz; g->max_degree = maxdeg; g->symmetric = sym ? 1 : 0;
+    g->h_rowptr.assign(rowptr, rowptr + n + 1);
     GN_CUDA(cudaGetDevice(&g->device));
     const size_t nnz_alloc = (size_t)std::max<int64_t>(nnz, 1);
     GN_CUDA(cudaMalloc(&g->d_rowptr, sizeof(int32_t) * (n + 1)));
@@ -161,18 +162,44 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
     b->M = M; b->n_inst = n_inst; b->nnz_total = nnz;
     b->n_tiles = (int32_t)((M + TILE - 1) / TILE);
     std::vector<int32_t> tile_inst(b->n_tiles);
+    std::vector<int64_t> tile_cost(b->n_tiles, 0);
     int32_t cur = 0;
     for (int32_t t = 0; t < b->n_tiles; ++t) {
         const int64_t r = (int64_t)t * TILE;
         while (cur + 1 < n_inst && inst[cur + 1].row0 <= r) ++cur;
         tile_inst[t] = cur;
+        // cost model: neighbour rows gathered by the tile (the only non-uniform work)
+        int32_t ii = cur;
+        for (int64_t g = r; g < std::min<int64_t>(r + TILE, M); ++g) {
+            while (ii + 1 < n_inst && inst[ii + 1].row0 <= g) ++ii;
+            const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
+            const int64_t nloc = g - inst[ii].row0;
+            tile_cost[t] += rp[nloc + 1] - rp[nloc];
+        }
+    }
+    // Processing order for the dynamic tile scheduler: tiles whose gather work exceeds 4x the mean
+    // (hub tiles of power-law graphs) are started first, heaviest first; all others keep the
+    // row-major order so that concurrently processed tiles share their trial's I' rows in L2.
+    std::vector<int32_t> order;
+    order.reserve(b->n_tiles);
+    {
+        const double mean = (double)nnz / std::max(1, b->n_tiles);
+        std::vector<int32_t> heavy;
+        for (int32_t t = 0; t < b->n_tiles; ++t)
+            if ((double)tile_cost[t] > 4.0 * mean + 1024.0) heavy.push_back(t);
+        std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t x, int32_t y) { return tile_cost[x] > tile_cost[y]; });
+        std::vector<char> is_heavy(b->n_tiles, 0);
+        for (int32_t t : heavy) { is_heavy[t] = 1; order.push_back(t); }
+        for (int32_t t = 0; t < b->n_tiles; ++t) if (!is_heavy[t]) order.push_back(t);
     }
     GN_CUDA(cudaGetDevice(&b->device));
     GN_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
     GN_CUDA(cudaMalloc(&b->d_inst, sizeof(GnInstance) * n_inst));
     GN_CUDA(cudaMalloc(&b->d_tile_inst, sizeof(int32_t) * b->n_tiles));
+    GN_CUDA(cudaMalloc(&b->d_tile_order, sizeof(int32_t) * b->n_tiles));
     GN_CUDA(cudaMemcpy(b->d_inst, inst.data(), sizeof(GnInstance) * n_inst, cudaMemcpyHostToDevice));
     GN_CUDA(cudaMemcpy(b->d_tile_inst, tile_inst.data(), sizeof(int32_t) * b->n_tiles, cudaMemcpyHostToDevice));
+    GN_CUDA(cudaMemcpy(b->d_tile_order, order.data(), sizeof(int32_t) * b->n_tiles, cudaMemcpyHostToDevice));
     *out = b;
     return GNODE_OK;
 }
@@ -181,6 +208,7 @@ extern "C" int gnode_batch_destroy(gnode_batch_t b) {
     if (!b) return GNODE_OK;
     cudaFree(b->d_inst);
     cudaFree(b->d_tile_inst);
+    cudaFree(b->d_tile_order);
     delete b;
     return GNODE_OK;
 }

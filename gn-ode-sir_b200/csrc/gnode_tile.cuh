@@ -6,6 +6,7 @@ namespace gnode {
 
 // Z = X W^T (X: swizzled 128x64 tile, W: [h][k]) ; dst = sigmoid(Z + b), swizzled.
 // 256 threads: thread (r0 = tid&63, q = tid>>6) owns rows r0, r0+64 x columns [16q,16q+16).
+template <bool FAST>
 __device__ __forceinline__ void gemm_sigmoid(const unsigned char* Xs, const float* Ws, const float* bs,
                                              unsigned char* dst, int tid) {
     if (tid >= 256) return;
@@ -31,10 +32,10 @@ __device__ __forceinline__ void gemm_sigmoid(const unsigned char* Xs, const floa
     for (int j = 0; j < 4; ++j) {
         const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * q + 4 * j);
         float4 o0, o1;
-        o0.x = sigmoidf_acc(a0[4 * j + 0] + bb.x); o0.y = sigmoidf_acc(a0[4 * j + 1] + bb.y);
-        o0.z = sigmoidf_acc(a0[4 * j + 2] + bb.z); o0.w = sigmoidf_acc(a0[4 * j + 3] + bb.w);
-        o1.x = sigmoidf_acc(a1[4 * j + 0] + bb.x); o1.y = sigmoidf_acc(a1[4 * j + 1] + bb.y);
-        o1.z = sigmoidf_acc(a1[4 * j + 2] + bb.z); o1.w = sigmoidf_acc(a1[4 * j + 3] + bb.w);
+        o0.x = sigmoid_t<FAST>(a0[4 * j + 0] + bb.x); o0.y = sigmoid_t<FAST>(a0[4 * j + 1] + bb.y);
+        o0.z = sigmoid_t<FAST>(a0[4 * j + 2] + bb.z); o0.w = sigmoid_t<FAST>(a0[4 * j + 3] + bb.w);
+        o1.x = sigmoid_t<FAST>(a1[4 * j + 0] + bb.x); o1.y = sigmoid_t<FAST>(a1[4 * j + 1] + bb.y);
+        o1.z = sigmoid_t<FAST>(a1[4 * j + 2] + bb.z); o1.w = sigmoid_t<FAST>(a1[4 * j + 3] + bb.w);
         sts4(dst, sw_off(r0, 4 * q + j), o0);
         sts4(dst, sw_off(r0 + 64, 4 * q + j), o1);
     }

@@ -1,0 +1,176 @@
+// tcgen05 (5th-gen tensor core) helpers for the node-wise H x H transform:
+//   dst = sigmoid(X W^T + b),  X: [128 rows x 64] fp32 tile, W: [64 x 64] fp32
+// computed as a 3xTF32 split product so that the result is fp32-accurate
+// (BASELINE.json north_star: "3xTF32 or fp32 so results stay within tolerance"):
+//   X = Xhi + Xlo,  W = Whi + Wlo   (hi = top 19 bits, lo = tf32(residual))
+//   X W^T ~= Xlo Whi^T + Xhi Wlo^T + Xhi Whi^T          (the lo*lo term is < 2^-22 relative)
+// Operands live in shared memory in the canonical UMMA K-major SWIZZLE_128B layout
+// (two K-blocks of 32 fp32; rows of 128 B; 16-B chunks XORed with row&7), the fp32
+// accumulator [128 lanes x 64 columns] lives in TMEM, tcgen05.mma is issued by one thread,
+// completion is signalled through an mbarrier by tcgen05.commit, and the four "row warps"
+// read the accumulator back with tcgen05.ld (lane == tile row) for the bias + sigmoid epilogue.
+#pragma once
+#include "gnode_common.cuh"
+
+namespace gnode {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one warp, .sync.aligned)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();      // a lost completion must fault, never hang the GPU
+    } while (!done);
+}
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout)
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 [0,14) | LBO>>4 [16,30) (ignored for
+// swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups | version=1 [46,48) | layout=2 [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::tf32: D=F32 [4,6)=1 | A=TF32 [7,10)=2 | B=TF32 [10,13)=2 | A,B K-major |
+// N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- 3xTF32 split
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_lo(float x) { return tf32_rna(x - tf32_hi(x)); }
+__device__ __forceinline__ float4 tf32_lo4(float4 x) { return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)); }
+__device__ __forceinline__ float4 tf32_hi4(float4 x) { return make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w)); }
+
+// byte offset of chunk c4 of row n in the 64-row B operand (K-block stride 8 KB)
+__device__ __forceinline__ int swb_off(int n, int c4) { return ((c4 >> 3) << 13) + (n << 7) + (((c4 & 7) ^ (n & 7)) << 4); }
+
+constexpr int TMEM_COLS = 64;
+
+struct Ctx {
+    uint32_t tmem;       // TMEM base address of the [128 x 64] fp32 accumulator
+    uint64_t* bar;       // mbarrier signalled by tcgen05.commit
+    uint32_t phase;      // parity of the next completion
+    uint32_t whi, wlo;   // shared-space addresses of the W operand tiles (hi, lo)
+};
+
+// W [64 x 64] fp32 (global, [out][in]) -> Whi / Wlo operand tiles. All threads; caller syncs.
+__device__ __forceinline__ void prepare_weights(const float* __restrict__ W, unsigned char* Whi, unsigned char* Wlo,
+                                                int tid, int nthreads) {
+    for (int idx = tid; idx < H * CHUNKS; idx += nthreads) {
+        const int n = idx >> 4, c4 = idx & 15;
+        const float4 w = ldg4(W + n * H + 4 * c4);
+        sts4(Whi, swb_off(n, c4), tf32_hi4(w));
+        sts4(Wlo, swb_off(n, c4), tf32_lo4(w));
+    }
+    fence_proxy_async();
+}
+
+// dst(Ls) = sigmoid(Xs W^T + b). Xs: raw fp32 tile (kept intact); Ls: scratch for Xlo, then the result.
+// Must be called by all NTHREADS threads; warps 0..3 are the row warps. Ends WITHOUT a block barrier:
+// the caller must __syncthreads() before other warps read Ls.
+template <bool FAST>
+__device__ __forceinline__ void gemm_sigmoid_tc(Ctx& cx, unsigned char* Xs, unsigned char* Ls, const float* bs, int tid) {
+    // 1. residual operand Xlo (same swizzled position as X)
+    for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
+        const int off = sw_off(idx >> 4, idx & 15);
+        sts4(Ls, off, tf32_lo4(lds4(Xs, off)));
+    }
+    fence_proxy_async();
+    __syncthreads();
+    // 2. one thread issues the 24 MMAs (M128 N64 K8 each) and commits to the mbarrier
+    if (tid == 0) {
+        fence_after_sync();
+        const uint32_t xs = smem_u32(Xs), ls = smem_u32(Ls);
+        constexpr uint32_t idesc = instr_desc_tf32(TILE, H);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t abase = (pass == 0) ? ls : xs;                 // Xlo, Xhi(raw: low 13 bits ignored), Xhi
+            const uint32_t bbase = (pass == 1) ? cx.wlo : cx.whi;        // Whi,  Wlo,                          Whi
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                                  // 8 K-steps of 8 tf32 (32 B)
+                const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
+                const uint32_t boff = ((k >> 2) << 13) + ((k & 3) << 5);
+                mma_tf32(cx.tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
+                acc = 1;
+            }
+        }
+        mma_commit(cx.bar);
+    }
+    // 3. row warps: accumulator -> registers -> bias + sigmoid -> Ls (thread == tile row)
+    if (tid < 128) {
+        mbar_wait(cx.bar, cx.phase);
+        __syncwarp();
+        fence_after_sync();
+        const int row = tid;
+        const uint32_t lane_base = cx.tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[16];
+            tmem_ld16(lane_base + 16 * c, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
+                float4 o;
+                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                sts4(Ls, sw_off(row, 4 * c + j), o);
+            }
+        }
+        fence_before_sync();
+    }
+    cx.phase ^= 1;
+}
+
+}  // namespace umma
+}  // namespace gnode

@@ -72,6 +72,10 @@ typedef struct {
 
 const char* gnode_last_error(void);
 int gnode_version(void);
+/* Kernel variant of the forward step: bit 0 = tcgen05 3xTF32 tensor-core transform (else fused FFMA),
+ * bit 1 = MUFU ex2/rcp sigmoid (else expf + IEEE division). Default: env GNODE_VARIANT or the build default. */
+int gnode_set_variant(int variant);
+int gnode_get_variant(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t gnode_launch_count(void);
 

@@ -1,0 +1,69 @@
+"""Parity of every forward kernel variant (FFMA / tcgen05 3xTF32, accurate / MUFU sigmoid)
+against the reference's outputs, and their agreement with one another."""
+import pytest
+import torch
+
+from _util import GOLDEN_CASES, Golden
+from oracle import gnode_oracle as orc
+from test_parity_gpu import DEV, dev_params, make_batch, run_cuda
+
+pytestmark = pytest.mark.gpu
+VARIANTS = {0: "ffma+expf", 1: "tcgen05+expf", 2: "ffma+mufu", 3: "tcgen05+mufu"}
+
+
+@pytest.fixture(scope="module")
+def gn():
+    import gn_ode_sir_b200 as g
+    g.build_library()
+    return g
+
+
+@pytest.fixture
+def variant(gn, request):
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
+    prev = L.gnode_get_variant()
+    _lib.check(L.gnode_set_variant(request.param), "gnode_set_variant")
+    yield request.param
+    L.gnode_set_variant(prev)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS), indirect=True, ids=list(VARIANTS.values()))
+@pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if "fbsocial" not in c])
+def test_variant_rollout_matches_reference(gn, variant, name):
+    g = Golden(name)
+    probs = run_cuda(gn, g)
+    err = (probs[:: g.tstride] - g.probs32).abs().max().item()
+    print("variant %d %s: max|cuda - reference| = %.3e" % (variant, name, err))
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS), indirect=True, ids=list(VARIANTS.values()))
+def test_variant_rhs_teacher_forced(gn, variant):
+    """One f(t,y) on oracle states: the 3xTF32 split product must be fp32-accurate (2e-6 scale-relative)."""
+    for name in ("sim_fbfood_b2", "sim_fbsocial_b1"):
+        g = Golden(name)
+        coo = orc.batch_coo(g.adjs, g.inst_graph)
+        _, traj = orc.forward(g.x, g.params, coo, orc.time_grid(g.maxTime, g.deltaT), return_traj=True)
+        batch = make_batch(gn, g)
+        W, b = g.params["odefunc.linear.weight"], g.params["odefunc.linear.bias"]
+        for k in (0, 38):
+            y = traj[k]
+            want = torch.stack(orc.rhs(y[0], y[1], y[2], g.x[:, 3].contiguous(), g.x[:, 4].contiguous(), W, b, coo))
+            got = gn.rollout.odefunc_eval(y.to(DEV), g.x[:, 3].contiguous().to(DEV), g.x[:, 4].contiguous().to(DEV),
+                                          batch, [W.to(DEV), b.to(DEV)] + [b.to(DEV)] * 6).cpu()
+            scale = want.abs().max().item()
+            err = (got - want).abs().max().item()
+            print("variant %d %s k=%d: rhs err %.3e (scale %.3e, rel %.2e)" % (variant, name, k, err, scale, err / scale))
+            assert err <= 2e-6 * scale, (name, k, err, scale)
+
+
+@pytest.mark.parametrize("variant", [1, 3], indirect=True, ids=["tcgen05+expf", "tcgen05+mufu"])
+def test_variant_large_graph_fp64(gn, variant):
+    g = Golden("sim_fbsocial_b1")
+    probs = run_cuda(gn, g)[:: g.tstride]
+    ref64 = g.probs64.double()
+    err_ours = (probs.double() - ref64).abs().max().item()
+    err_ref = (g.probs32.double() - ref64).abs().max().item()
+    print("variant %d fb-social: err vs fp64 ours %.3e, reference fp32 %.3e" % (variant, err_ours, err_ref))
+    assert err_ours <= max(1e-5, 2.0 * err_ref), (err_ours, err_ref)
