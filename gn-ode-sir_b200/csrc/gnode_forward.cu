@@ -20,7 +20,7 @@
 #include "gnode_umma.cuh"
 
 #ifndef GNODE_DEFAULT_VARIANT
-#define GNODE_DEFAULT_VARIANT 0
+#define GNODE_DEFAULT_VARIANT 1
 #endif
 
 namespace gnode {
@@ -39,6 +39,7 @@ struct StepArgs {
     int64_t ldx;
     float* probs;         // [M][3] slice of the produced state, or null
     float dt;
+    int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
     int* counter;         // dynamic tile scheduler (one zeroed int per launch) or null = static striding
     gnode_params_t p;
 };
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
                 if (valid) {
                     const size_t off = (size_t)g * H + 4 * l;
                     const float4 ipo = ldg4(a.ip_in + off);
-                    const float4 s = lds4(Xs, sw_off(rr, l));
+                    // the tensor path replaces the operand tile by its tf32 hi part: re-read S_k (L2 hit)
+                    const float4 s = TC ? ldg4(a.y_in + off) : lds4(Xs, sw_off(rr, l));
                     const float4 sp = lds4(SPs, sw_off(rr, l));
                     const float4 iv = ldg4_stream(a.y_in + plane + off);
                     const float4 rv = ldg4_stream(a.y_in + 2 * plane + off);
@@ -264,6 +266,312 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused Euler step, tensor-core path (the production kernel for MODE_STEP).
+//
+// Per 128-row tile (2 CTAs of 512 threads per SM; all block barriers are __syncthreads):
+//   P1  S_k tile (prefetched into registers during the previous tile's second GEMM) -> tf32 hi/lo
+//       operand tiles; the tile's rowptr slice -> shared memory                              | S1
+//   P2  one thread issues GEMM1 (tcgen05, 32 MMAs); meanwhile all threads stage the tile's colidx
+//       slice (as global row ids) in shared memory; then all 16 warps run the S' epilogue     | S2
+//   P3  row-per-half-warp: neighbour sum with indices from shared memory (no dependent index
+//       round trips), SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles            | S3
+//   P4  one thread issues GEMM2; all threads prefetch the next tile's S rows into registers; all
+//       warps run the I' epilogue into the staging tile                                       | S4
+//   P5  coalesced store of I'_{k+1}                                                           | S5
+constexpr int CSR_CAP = 2816;                   // colidx entries staged per tile (rest read from HBM/L2)
+constexpr int T_X = 0;                          // 32 KB  A operand hi  (parks the neighbour sums between the two row phases)
+constexpr int T_L = 32768;                      // 32 KB  A operand lo / S' / I' staging
+constexpr int T_WHI = 65536;                    // 16 KB
+constexpr int T_WLO = T_WHI + H * H * 4;        // 16 KB
+constexpr int T_B = T_WLO + H * H * 4;          // bias [64]
+constexpr int T_W3 = T_B + H * 4;               // linear3.weight [4][64]
+constexpr int T_SMALL = T_W3 + 4 * H * 4;       // b3[4], w2[4], b2
+constexpr int T_MBAR = T_SMALL + 64;            // mbarrier (8) + tmem slot (4) + next-tile slot (4)
+constexpr int T_BG = T_MBAR + 16;               // beta[TILE], gamma[TILE] of the tile
+constexpr int T_RP = T_BG + 2 * TILE * 4;       // rowptr slice [TILE + 1] (+pad)
+constexpr int T_CI = T_RP + 544;                // colidx slice [CSR_CAP] as global row ids
+constexpr int T_TOTAL = T_CI + CSR_CAP * 4 + 1024;
+static_assert(2 * (T_TOTAL + 1024) <= 232448, "two CTAs per SM must fit in shared memory");
+
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// decoder + softmax with a 20-shuffle butterfly: after 4 halving exchange stages lane l of the
+// half-warp holds the complete pre-activation hid[c = l>>2][m = l&3] (c = 3 is padding).
+__device__ __forceinline__ void decode_row_bfly(float4 s, float4 i, float4 r, const float* W3s, const float* small,
+                                                int l, int lane, bool valid, float* probs_row) {
+    float v[16];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const float4 w = *reinterpret_cast<const float4*>(W3s + m * H + 4 * l);
+        v[m] = dot4(s, w); v[4 + m] = dot4(i, w); v[8 + m] = dot4(r, w); v[12 + m] = 0.f;
+    }
+    const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0, b1 = (l & 2) != 0, b0 = (l & 1) != 0;
+    float a8[8], a4[4], a2[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a8[k] = (b3 ? v[8 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b3 ? v[k] : v[8 + k], 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a4[k] = (b2 ? a8[4 + k] : a8[k]) + __shfl_xor_sync(0xffffffffu, b2 ? a8[k] : a8[4 + k], 4);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) a2[k] = (b1 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b1 ? a4[k] : a4[2 + k], 2);
+    const float hid = (b0 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? a2[0] : a2[1], 1);
+    const int m = l & 3;
+    float t = small[4 + m] * fmaxf(hid + small[m], 0.f);          // w2[m] * relu(hid + b3[m])
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    const float o = t + small[8];
+    const int hb = lane & 16;
+    const float oS = __shfl_sync(0xffffffffu, o, hb + 0), oI = __shfl_sync(0xffffffffu, o, hb + 4),
+                oR = __shfl_sync(0xffffffffu, o, hb + 8);
+    // softmax; exp(x) = 2^(x log2 e) with x <= 0 (absolute error of each probability < 4e-7)
+    const float mx = fmaxf(oS, fmaxf(oI, oR));
+    const float eS = ex2_approx((oS - mx) * 1.4426950408889634f), eI = ex2_approx((oI - mx) * 1.4426950408889634f),
+                eR = ex2_approx((oR - mx) * 1.4426950408889634f);
+    const float inv = rcp_approx(eS + eI + eR);
+    if (valid && l < 3) probs_row[l] = (l == 0 ? eS : (l == 1 ? eI : eR)) * inv;
+}
+
+// Neighbour sum of one row with the tile's indices staged in shared memory: full batches of 8
+// unpredicated loads, one predicated tail batch. Sequential ascending-column accumulation.
+__device__ __forceinline__ float4 gather_smem(const float* __restrict__ lane_base, const int* cp, int deg) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 8 <= deg; j += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ldg4(lane_base + (size_t)(unsigned)cp[j + k] * H);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+    // tail (< 8 neighbours): one unpredicated batch of 4 and up to 3 predicated loads, all issued
+    // before the first add so that they share one memory round trip
+    const int rem = deg - j;
+    const bool four = rem >= 4;
+    const int j3 = j + (four ? 4 : 0), r3 = rem & 3;
+    float4 v4[4], v3[3];
+    if (four) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v4[k] = ldg4(lane_base + (size_t)(unsigned)cp[j + k] * H);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        v3[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < r3) v3[k] = ldg4(lane_base + (size_t)(unsigned)cp[j3 + k] * H);
+    }
+    if (four) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc.x += v4[k].x; acc.y += v4[k].y; acc.z += v4[k].z; acc.w += v4[k].w; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        if (k < r3) { acc.x += v3[k].x; acc.y += v3[k].y; acc.z += v3[k].z; acc.w += v3[k].w; }
+    return acc;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Xs = smem + T_X;
+    unsigned char* Ls = smem + T_L;
+    float* bs = reinterpret_cast<float*>(smem + T_B);
+    float* W3s = reinterpret_cast<float*>(smem + T_W3);
+    float* small = reinterpret_cast<float*>(smem + T_SMALL);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T_MBAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + T_MBAR + 8);
+    int* seq_slot = reinterpret_cast<int*>(smem + T_MBAR + 12);
+    float* bg_s = reinterpret_cast<float*>(smem + T_BG);
+    int* rp_s = reinterpret_cast<int*>(smem + T_RP);
+    int* ci_s = reinterpret_cast<int*>(smem + T_CI);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l = tid & 15, hw = tid >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    const int n_tiles = a.bv.n_tiles;
+    // every tile access of this thread is chunk l of rows hw + 32*i: one swizzled offset + i * 4 KB
+    const int off0 = sw_off(hw, l);
+
+    umma::prepare_weights(a.p.lin_w, smem + T_WHI, smem + T_WLO, tid, NTHREADS);
+    if (warp == 0) umma::tmem_alloc(tslot, umma::TMEM_COLS);
+    if (tid == 0) {
+        umma::mbar_init(mbar, 1);
+        *seq_slot = a.counter ? atomicAdd(a.counter, 1) : (int)blockIdx.x;
+    }
+    umma::fence_before_sync();
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
+    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+    if (tid == 0) small[8] = a.p.s2_b[0];
+    __syncthreads();
+    umma::fence_after_sync();
+    umma::Ctx cx;
+    cx.tmem = *tslot; cx.bar = mbar; cx.phase = 0;
+    cx.whi = umma::smem_u32(smem + T_WHI); cx.wlo = umma::smem_u32(smem + T_WLO);
+    const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
+
+    int seq = *seq_slot;
+    // HBM -> L2 one tile ahead: the S tile (operand of GEMM1) and the own-row operands of the row phases
+    auto prefetch_tile = [&](int sq) {
+        if (sq < n_tiles && tid == 0 && !(a.dbg & 32)) {
+            const int t0 = a.bv.tile_order[sq] * TILE;
+            const uint32_t bytes = (uint32_t)min(TILE, M - t0) * H * 4;
+            prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
+            prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
+            prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
+            prefetch_l2_bulk(a.ip_in + (size_t)t0 * H, bytes);
+        }
+    };
+    prefetch_tile(seq);
+
+    while (seq < n_tiles) {
+        const int tile = a.bv.tile_order[seq];
+        const int tile0 = tile * TILE;
+        const int nrows = min(TILE, M - tile0);
+        const int inst0 = a.bv.tile_inst[tile];
+        const int i_row0 = a.bv.inst[inst0].row0;
+        const bool single = (tile0 + nrows <= i_row0 + a.bv.inst[inst0].n);   // whole tile inside one instance
+        const int32_t* i_colidx = a.bv.inst[inst0].colidx;
+
+        // ---- P1: operand tiles for GEMM1 (S_k rows from L2); rowptr slice, beta/gamma of the tile
+        {
+            const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+            float4 sreg[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                sreg[i] = (hw + 32 * i < nrows) ? ldg4(src + (size_t)i * 32 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 hi, lo;
+                umma::tf32_split4(sreg[i], hi, lo);
+                sts4(Xs, off0 + i * 4096, hi);
+                sts4(Ls, off0 + i * 4096, lo);
+            }
+        }
+        umma::fence_proxy_async();
+        if (single && tid <= nrows) rp_s[tid] = a.bv.inst[inst0].rowptr[tile0 - i_row0 + tid];
+        if (tid >= 256 && tid < 256 + nrows) bg_s[tid - 256] = a.beta[tile0 + tid - 256];
+        if (tid >= 384 && tid < 384 + nrows) bg_s[TILE + tid - 384] = a.gamma[tile0 + tid - 384];
+        __syncthreads();                                                        // S1
+        // ---- P2: GEMM1 || colidx staging ; S' epilogue
+        if (!(a.dbg & 16) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
+        int ebase = 0;
+        if (single) {
+            ebase = rp_s[0];
+            const int ecnt = min(rp_s[nrows] - ebase, CSR_CAP);
+            for (int j = tid; j < ecnt; j += NTHREADS) ci_s[j] = i_colidx[ebase + j] + i_row0;
+        }
+        if (!(a.dbg & 16)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
+        __syncthreads();                                                        // S2
+        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile
+        {
+            const float* lane_base = a.ip_in + 4 * l;
+            int inst = inst0;
+#pragma unroll 1
+            for (int it = 0; it < TILE / 32; ++it) {
+                const int rr = hw + 32 * it;
+                const bool valid = rr < nrows;
+                float4 acc;
+                if (single) {
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) {
+                        const int e_rel = rp_s[rr] - ebase, deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr];
+                        if (e_rel + deg <= CSR_CAP) {
+                            acc = gather_smem(lane_base, ci_s + e_rel, deg);
+                        } else {                             // hub tile: indices beyond the staged slice
+                            for (int j = 0; j < deg; ++j) {
+                                const int c = i_colidx[ebase + e_rel + j] + i_row0;
+                                const float4 v = ldg4(lane_base + (size_t)c * H);
+                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                            }
+                        }
+                    }
+                } else {                                     // tile spans several (small) instances
+                    int row0 = 0, e0 = 0, deg = 0;
+                    const int32_t* ci = nullptr;
+                    if (valid) {
+                        const int g = tile0 + rr;
+                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                        const GnInstance I = a.bv.inst[inst];
+                        row0 = I.row0; ci = I.colidx;
+                        e0 = I.rowptr[g - row0];
+                        deg = I.rowptr[g - row0 + 1] - e0;
+                    }
+                    acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                }
+                sts4(Xs, off0 + it * 4096, acc);
+            }
+        }
+        __syncwarp();
+        // ---- P3b: SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles
+#pragma unroll 1
+        for (int it = 0; it < TILE / 32; ++it) {
+            const int rr = hw + 32 * it;
+            const bool valid = rr < nrows;
+            const size_t off = (size_t)(tile0 + (valid ? rr : 0)) * H + 4 * l;
+            float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
+            if (valid) {
+                float4 s = make_float4(1.f, 1.f, 1.f, 1.f), iv = s, rv = s, ipo = s;
+                if (!(a.dbg & 4)) {
+                    s = ldg4(a.y_in + off);
+                    iv = ldg4_stream(a.y_in + plane + off);
+                    rv = ldg4_stream(a.y_in + 2 * plane + off);
+                    ipo = ldg4(a.ip_in + off);
+                }
+                const float4 acc = lds4(Xs, off0 + it * 4096);
+                const float4 sp = lds4(Ls, off0 + it * 4096);
+                const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
+#define GN_COMP(c)                                                                  \
+    {                                                                               \
+        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
+        const float dR = __fmul_rn(ga, ipo.c);                                      \
+        const float dI = __fsub_rn(-dS, dR);                                        \
+        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
+        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
+        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
+    }
+                GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+#undef GN_COMP
+                stg4_stream(a.y_out + off, sn);
+                stg4_stream(a.y_out + plane + off, in_);
+                stg4_stream(a.y_out + 2 * plane + off, rn);
+                float4 hi, lo;
+                umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
+                sts4(Xs, off0 + it * 4096, hi);
+                sts4(Ls, off0 + it * 4096, lo);
+            }
+            if (a.probs != nullptr && !(a.dbg & 1))
+                decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
+        }
+        if (tid == 0) *seq_slot = a.counter ? atomicAdd(a.counter, 1) : seq + (int)gridDim.x;
+        umma::fence_proxy_async();
+        __syncthreads();                                                        // S3
+        // ---- P4: GEMM2 || prefetch of the next tile ; I' epilogue
+        if (!(a.dbg & 8) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
+        const int seq_next = *seq_slot;
+        prefetch_tile(seq_next);
+        if (!(a.dbg & 8)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
+        __syncthreads();                                                        // S4
+        // ---- P5: coalesced store of I'_{k+1}
+        {
+            float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (hw + 32 * i < nrows) stg4(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096));
+        }
+        __syncthreads();                                                        // S5
+        seq = seq_next;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
+}
+
 // 0 = FFMA + accurate sigmoid ... 3 = tcgen05 + MUFU sigmoid; chosen by gnode_set_variant() / GNODE_VARIANT
 static int g_variant = -1;
 
@@ -288,9 +596,25 @@ static int launch_step_v(const gnode_batch* b, const StepArgs& a, cudaStream_t s
     return GNODE_OK;
 }
 
+template <bool FAST>
+static int launch_step_tc(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(step_tc_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const int grid = std::min(b->n_tiles, 2 * b->sm_count);
+    step_tc_kernel<FAST><<<grid, NTHREADS, T_TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
 template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
-    switch (current_variant()) {
+    const int var = current_variant();
+    if (MODE == MODE_STEP && (var & VAR_TC) && !getenv("GNODE_GENERIC_STEP"))
+        return (var & VAR_FASTSIG) ? launch_step_tc<true>(b, a, stream) : launch_step_tc<false>(b, a, stream);
+    switch (var) {
         case 0: return launch_step_v<MODE, 0>(b, a, stream);
         case 1: return launch_step_v<MODE, 1>(b, a, stream);
         case 2: return launch_step_v<MODE, 2>(b, a, stream);
@@ -358,7 +682,8 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     a.y_in = nullptr; a.ip_in = nullptr;
     a.y_out = state(0); a.ip_out = ip[0];
     a.probs = probs; a.dt = 0.f;
-    a.counter = counters;
+    a.dbg = getenv("GNODE_DBG") ? atoi(getenv("GNODE_DBG")) : 0;
+    a.counter = (a.dbg & 64) ? nullptr : counters;
     int rc = launch_step<MODE_ENCODE>(b, a, stream);
     if (rc) return rc;
     for (int k = 0; k + 1 < T; ++k) {
@@ -366,7 +691,7 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
         a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
         a.probs = probs + (size_t)(k + 1) * M * 3;
         a.dt = dt_host[k];
-        a.counter = (k + 1 < 1024) ? counters + (k + 1) : nullptr;
+        a.counter = (k + 1 < 1024 && !(a.dbg & 64)) ? counters + (k + 1) : nullptr;
         rc = launch_step<MODE_STEP>(b, a, stream);
         if (rc) return rc;
     }
@@ -384,7 +709,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f; a.counter = nullptr;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;

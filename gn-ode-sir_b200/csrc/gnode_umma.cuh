@@ -2,8 +2,8 @@
 //   dst = sigmoid(X W^T + b),  X: [128 rows x 64] fp32 tile, W: [64 x 64] fp32
 // computed as a 3xTF32 split product so that the result is fp32-accurate
 // (BASELINE.json north_star: "3xTF32 or fp32 so results stay within tolerance"):
-//   X = Xhi + Xlo,  W = Whi + Wlo   (hi = top 19 bits, lo = tf32(residual))
-//   X W^T ~= Xlo Whi^T + Xhi Wlo^T + Xhi Whi^T          (the lo*lo term is < 2^-22 relative)
+//   X = Xhi + Xlo,  W = Whi + Wlo   (hi = rna_tf32(x), lo = rna_tf32(x - hi); |x - hi - lo| <= 2^-23 |x|)
+//   X W^T = Xlo Wlo^T + Xlo Whi^T + Xhi Wlo^T + Xhi Whi^T   (all four terms: per-product error ~2^-22)
 // Operands live in shared memory in the canonical UMMA K-major SWIZZLE_128B layout
 // (two K-blocks of 32 fp32; rows of 128 B; 16-B chunks XORed with row&7), the fp32
 // accumulator [128 lanes x 64 columns] lives in TMEM, tcgen05.mma is issued by one thread,
@@ -80,16 +80,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// ---- 3xTF32 split
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// ---- TF32 split: x = hi + lo + O(2^-23 |x|), hi = rna_tf32(x), lo = rna_tf32(x - hi); both have their
+// low 13 mantissa bits zero, so the tensor core (which reads only the top 19 bits) sees them exactly.
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ float tf32_lo(float x) { return tf32_rna(x - tf32_hi(x)); }
-__device__ __forceinline__ float4 tf32_lo4(float4 x) { return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)); }
-__device__ __forceinline__ float4 tf32_hi4(float4 x) { return make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w)); }
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) { hi = tf32_rna(x); lo = tf32_rna(x - hi); }
+__device__ __forceinline__ void tf32_split4(float4 x, float4& hi, float4& lo) {
+    tf32_split(x.x, hi.x, lo.x); tf32_split(x.y, hi.y, lo.y); tf32_split(x.z, hi.z, lo.z); tf32_split(x.w, hi.w, lo.w);
+}
 
 // byte offset of chunk c4 of row n in the 64-row B operand (K-block stride 8 KB)
 __device__ __forceinline__ int swb_off(int n, int c4) { return ((c4 >> 3) << 13) + (n << 7) + (((c4 & 7) ^ (n & 7)) << 4); }
@@ -108,68 +109,74 @@ __device__ __forceinline__ void prepare_weights(const float* __restrict__ W, uns
                                                 int tid, int nthreads) {
     for (int idx = tid; idx < H * CHUNKS; idx += nthreads) {
         const int n = idx >> 4, c4 = idx & 15;
-        const float4 w = ldg4(W + n * H + 4 * c4);
-        sts4(Whi, swb_off(n, c4), tf32_hi4(w));
-        sts4(Wlo, swb_off(n, c4), tf32_lo4(w));
+        float4 hi, lo;
+        tf32_split4(ldg4(W + n * H + 4 * c4), hi, lo);
+        sts4(Whi, swb_off(n, c4), hi);
+        sts4(Wlo, swb_off(n, c4), lo);
     }
     fence_proxy_async();
 }
 
-// dst(Ls) = sigmoid(Xs W^T + b). Xs: raw fp32 tile (kept intact); Ls: scratch for Xlo, then the result.
-// Must be called by all NTHREADS threads; warps 0..3 are the row warps. Ends WITHOUT a block barrier:
-// the caller must __syncthreads() before other warps read Ls.
+// One thread: D[128x64] = Xlo Wlo^T + Xlo Whi^T + Xhi Wlo^T + Xhi Whi^T (small terms first), then commit.
+// 4 passes x 8 K-steps of tcgen05.mma kind::tf32 (M128 N64 K8).
+__device__ __forceinline__ void issue_split_gemm(const Ctx& cx, uint32_t xhi, uint32_t xlo) {
+    fence_after_sync();
+    constexpr uint32_t idesc = instr_desc_tf32(TILE, H);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const uint32_t abase = (pass < 2) ? xlo : xhi;
+        const uint32_t bbase = (pass == 0 || pass == 2) ? cx.wlo : cx.whi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                                  // 8 K-steps of 8 tf32 (32 B)
+            const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
+            const uint32_t boff = ((k >> 2) << 13) + ((k & 3) << 5);
+            mma_tf32(cx.tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
+            acc = 1;
+        }
+    }
+    mma_commit(cx.bar);
+}
+
+// All 16 warps: wait for the accumulator, then warp w converts the [32 lanes (w&3)] x [16 columns (w>>2)]
+// block: dst = sigmoid(acc + b) written thread-per-row into the swizzled tile dst.
+template <bool FAST>
+__device__ __forceinline__ void epilogue_sigmoid(Ctx& cx, unsigned char* dst, const float* bs, int warp, int lane) {
+    if (lane == 0) mbar_wait(cx.bar, cx.phase);          // one poller per warp
+    __syncwarp();
+    fence_after_sync();
+    const int q = warp & 3, cq = warp >> 2;
+    float v[16];
+    tmem_ld16(cx.tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+    const int row = q * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+        float4 o;
+        o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+        o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+        sts4(dst, sw_off(row, 4 * cq + j), o);
+    }
+    fence_before_sync();
+    cx.phase ^= 1;
+}
+
+// dst(Ls) = sigmoid(Xs W^T + b). Xs: fp32 tile, replaced in place by its tf32 hi part; Ls: scratch for the
+// lo part, then the result. Called by all NTHREADS threads. Ends WITHOUT a block barrier: the caller must
+// __syncthreads() before other warps read Ls.
 template <bool FAST>
 __device__ __forceinline__ void gemm_sigmoid_tc(Ctx& cx, unsigned char* Xs, unsigned char* Ls, const float* bs, int tid) {
-    // 1. residual operand Xlo (same swizzled position as X)
     for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
         const int off = sw_off(idx >> 4, idx & 15);
-        sts4(Ls, off, tf32_lo4(lds4(Xs, off)));
+        float4 hi, lo;
+        tf32_split4(lds4(Xs, off), hi, lo);
+        sts4(Xs, off, hi);
+        sts4(Ls, off, lo);
     }
     fence_proxy_async();
     __syncthreads();
-    // 2. one thread issues the 24 MMAs (M128 N64 K8 each) and commits to the mbarrier
-    if (tid == 0) {
-        fence_after_sync();
-        const uint32_t xs = smem_u32(Xs), ls = smem_u32(Ls);
-        constexpr uint32_t idesc = instr_desc_tf32(TILE, H);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t abase = (pass == 0) ? ls : xs;                 // Xlo, Xhi(raw: low 13 bits ignored), Xhi
-            const uint32_t bbase = (pass == 1) ? cx.wlo : cx.whi;        // Whi,  Wlo,                          Whi
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {                                  // 8 K-steps of 8 tf32 (32 B)
-                const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
-                const uint32_t boff = ((k >> 2) << 13) + ((k & 3) << 5);
-                mma_tf32(cx.tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
-                acc = 1;
-            }
-        }
-        mma_commit(cx.bar);
-    }
-    // 3. row warps: accumulator -> registers -> bias + sigmoid -> Ls (thread == tile row)
-    if (tid < 128) {
-        mbar_wait(cx.bar, cx.phase);
-        __syncwarp();
-        fence_after_sync();
-        const int row = tid;
-        const uint32_t lane_base = cx.tmem + ((uint32_t)((tid >> 5) * 32) << 16);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float v[16];
-            tmem_ld16(lane_base + 16 * c, v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
-                float4 o;
-                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
-                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
-                sts4(Ls, sw_off(row, 4 * c + j), o);
-            }
-        }
-        fence_before_sync();
-    }
-    cx.phase ^= 1;
+    if (tid == 0) issue_split_gemm(cx, smem_u32(Xs), smem_u32(Ls));
+    epilogue_sigmoid<FAST>(cx, Ls, bs, tid >> 5, tid & 31);
 }
 
 }  // namespace umma
