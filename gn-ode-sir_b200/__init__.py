@@ -7,4 +7,4 @@ from . import _lib                                             # noqa: F401
 from ._build import LIB_PATH, build_library                    # noqa: F401
 from .graph import BatchCache, DeviceBatch, DeviceGraph        # noqa: F401
 from . import rollout                                          # noqa: F401  (rollout.rollout / .aggregate / .odefunc_eval)
-from . import ode_sim, ode_ngraphs                             # noqa: F401
+from . import ode_sim, ode_ngraphs, parallel, synth, harness    # noqa: F401

@@ -1,0 +1,84 @@
+"""Host-side logic of the trial-sharded data parallelism, world_size 2 over gloo on CPU
+(the CUDA rollout itself is covered by the -m gpu tests; here a tiny torch model stands in)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gn_ode_sir_b200  # noqa: F401
+from gn_ode_sir_b200 import parallel
+
+
+def test_shard_trials_partitions_exactly():
+    for n in (0, 1, 7, 8, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_trials(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_instances_balances_by_node_count():
+    sizes = [62] * 36 + [620] * 36 + [1893] * 36 + [2905] * 36 + [7066] * 36      # the five training graphs
+    parts = parallel.shard_instances(sizes, 8)
+    assert sorted(i for p in parts for i in p) == list(range(len(sizes)))
+    loads = [sum(sizes[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(sizes)
+    assert all(p == sorted(p) for p in parts)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # deliberately different initial weights per rank
+    model = torch.nn.Linear(5, 3)
+    parallel.broadcast_parameters(model, src=0)
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10.0
+    lo, hi = parallel.shard_trials(8, world, rank)
+    model.zero_grad()
+    (model(x[lo:hi]) ** 2).sum().backward()
+    parallel.allreduce_gradients(model.parameters())
+    out[rank] = (model.weight.detach().clone(), model.weight.grad.clone(), model.bias.grad.clone())
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_equals_single_process_gloo_ws2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    w0, gw0, gb0 = out[0]
+    w1, gw1, gb1 = out[1]
+    assert torch.equal(w0, w1)                          # broadcast made the replicas identical
+    assert torch.equal(gw0, gw1) and torch.equal(gb0, gb1)
+    ref = torch.nn.Linear(5, 3)
+    with torch.no_grad():
+        ref.weight.copy_(w0)
+        ref.bias.zero_()
+    # bias value does not enter d/dW of sum((Wx+b)^2) only through the residual; rebuild exactly
+    torch.manual_seed(100)
+    ref = torch.nn.Linear(5, 3)
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10.0
+    (ref(x) ** 2).sum().backward()
+    assert torch.allclose(gw0, ref.weight.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(gb0, ref.bias.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_allreduce_is_noop_without_process_group():
+    m = torch.nn.Linear(2, 2)
+    m(torch.ones(1, 2)).sum().backward()
+    g = m.weight.grad.clone()
+    parallel.allreduce_gradients(m.parameters())
+    assert torch.equal(g, m.weight.grad)
