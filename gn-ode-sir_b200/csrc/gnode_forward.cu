@@ -20,7 +20,7 @@
 #include "gnode_umma.cuh"
 
 #ifndef GNODE_DEFAULT_VARIANT
-#define GNODE_DEFAULT_VARIANT 1
+#define GNODE_DEFAULT_VARIANT 3
 #endif
 
 namespace gnode {
@@ -39,6 +39,7 @@ struct StepArgs {
     int64_t ldx;
     float* probs;         // [M][3] slice of the produced state, or null
     float dt;
+    long long* tbuf;      // phase timing accumulators (debug, env GNODE_DBG bit 7) or null
     int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
     int* counter;         // dynamic tile scheduler (one zeroed int per launch) or null = static striding
     gnode_params_t p;
@@ -338,13 +339,13 @@ __device__ __forceinline__ void decode_row_bfly(float4 s, float4 i, float4 r, co
 
 // Neighbour sum of one row with the tile's indices staged in shared memory: full batches of 8
 // unpredicated loads, one predicated tail batch. Sequential ascending-column accumulation.
-__device__ __forceinline__ float4 gather_smem(const float* __restrict__ lane_base, const int* cp, int deg) {
+__device__ __forceinline__ float4 gather_smem(const float* __restrict__ lane_base, const int* cp, int deg, uint64_t pol) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = 0;
     for (; j + 8 <= deg; j += 8) {
         float4 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = ldg4(lane_base + (size_t)(unsigned)cp[j + k] * H);
+        for (int k = 0; k < 8; ++k) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
     }
@@ -356,12 +357,12 @@ __device__ __forceinline__ float4 gather_smem(const float* __restrict__ lane_bas
     float4 v4[4], v3[3];
     if (four) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v4[k] = ldg4(lane_base + (size_t)(unsigned)cp[j + k] * H);
+        for (int k = 0; k < 4; ++k) v4[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         v3[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < r3) v3[k] = ldg4(lane_base + (size_t)(unsigned)cp[j3 + k] * H);
+        if (k < r3) v3[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j3 + k] * H, pol);
     }
     if (four) {
 #pragma unroll
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
     const int n_tiles = a.bv.n_tiles;
     // every tile access of this thread is chunk l of rows hw + 32*i: one swizzled offset + i * 4 KB
     const int off0 = sw_off(hw, l);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
     umma::prepare_weights(a.p.lin_w, smem + T_WHI, smem + T_WLO, tid, NTHREADS);
     if (warp == 0) umma::tmem_alloc(tslot, umma::TMEM_COLS);
@@ -424,11 +426,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
             prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
             prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
             prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
-            prefetch_l2_bulk(a.ip_in + (size_t)t0 * H, bytes);
+            prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
+            // look-ahead: the same rows of the NEXT instance (trial), so that its gathers find I' in L2
+            const int ahead = t0 + a.bv.inst[a.bv.tile_inst[a.bv.tile_order[sq]]].n;
+            if (ahead < M) prefetch_l2_bulk_hint(a.ip_in + (size_t)ahead * H, (uint32_t)min(TILE, M - ahead) * H * 4, pol_keep);
         }
     };
     prefetch_tile(seq);
 
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define GN_TICK(i) if (a.tbuf && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
     while (seq < n_tiles) {
         const int tile = a.bv.tile_order[seq];
         const int tile0 = tile * TILE;
@@ -458,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
         if (tid >= 256 && tid < 256 + nrows) bg_s[tid - 256] = a.beta[tile0 + tid - 256];
         if (tid >= 384 && tid < 384 + nrows) bg_s[TILE + tid - 384] = a.gamma[tile0 + tid - 384];
         __syncthreads();                                                        // S1
+        GN_TICK(0)
         // ---- P2: GEMM1 || colidx staging ; S' epilogue
         if (!(a.dbg & 16) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
         int ebase = 0;
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
         }
         if (!(a.dbg & 16)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
         __syncthreads();                                                        // S2
+        GN_TICK(1)
         // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile
         {
             const float* lane_base = a.ip_in + 4 * l;
@@ -482,11 +492,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
                     if (valid) {
                         const int e_rel = rp_s[rr] - ebase, deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr];
                         if (e_rel + deg <= CSR_CAP) {
-                            acc = gather_smem(lane_base, ci_s + e_rel, deg);
+                            acc = gather_smem(lane_base, ci_s + e_rel, deg, pol_keep);
                         } else {                             // hub tile: indices beyond the staged slice
                             for (int j = 0; j < deg; ++j) {
                                 const int c = i_colidx[ebase + e_rel + j] + i_row0;
-                                const float4 v = ldg4(lane_base + (size_t)c * H);
+                                const float4 v = ldg4_hint(lane_base + (size_t)c * H, pol_keep);
                                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                             }
                         }
@@ -508,6 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
             }
         }
         __syncwarp();
+        GN_TICK(2)
         // ---- P3b: SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles
 #pragma unroll 1
         for (int it = 0; it < TILE / 32; ++it) {
@@ -518,10 +529,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
             if (valid) {
                 float4 s = make_float4(1.f, 1.f, 1.f, 1.f), iv = s, rv = s, ipo = s;
                 if (!(a.dbg & 4)) {
-                    s = ldg4(a.y_in + off);
-                    iv = ldg4_stream(a.y_in + plane + off);
-                    rv = ldg4_stream(a.y_in + 2 * plane + off);
-                    ipo = ldg4(a.ip_in + off);
+                    s = ldg4_hint(a.y_in + off, pol_stream);
+                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
+                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
+                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
                 }
                 const float4 acc = lds4(Xs, off0 + it * 4096);
                 const float4 sp = lds4(Ls, off0 + it * 4096);
@@ -537,9 +548,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
     }
                 GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
 #undef GN_COMP
-                stg4_stream(a.y_out + off, sn);
-                stg4_stream(a.y_out + plane + off, in_);
-                stg4_stream(a.y_out + 2 * plane + off, rn);
+                stg4_hint(a.y_out + off, sn, pol_stream);
+                stg4_hint(a.y_out + plane + off, in_, pol_stream);
+                stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
                 float4 hi, lo;
                 umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
                 sts4(Xs, off0 + it * 4096, hi);
@@ -548,32 +559,382 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
             if (a.probs != nullptr && !(a.dbg & 1))
                 decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
         }
+        GN_TICK(3)
         if (tid == 0) *seq_slot = a.counter ? atomicAdd(a.counter, 1) : seq + (int)gridDim.x;
         umma::fence_proxy_async();
         __syncthreads();                                                        // S3
+        GN_TICK(4)
         // ---- P4: GEMM2 || prefetch of the next tile ; I' epilogue
         if (!(a.dbg & 8) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
         const int seq_next = *seq_slot;
         prefetch_tile(seq_next);
         if (!(a.dbg & 8)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
         __syncthreads();                                                        // S4
+        GN_TICK(5)
         // ---- P5: coalesced store of I'_{k+1}
         {
             float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (hw + 32 * i < nrows) stg4(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096));
+                if (hw + 32 * i < nrows) stg4_hint(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096), pol_stream);
         }
         __syncthreads();                                                        // S5
+        GN_TICK(6)
         seq = seq_next;
     }
+    if (a.tbuf && tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
+#undef GN_TICK
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised fused Euler step (1 CTA of 640 threads per SM, two tile slots in flight).
+//
+//   PE-A group (4 warps = the four TMEM lane quarters): for tile t in slot t&1 (after slot_free)
+//       S_k rows -> tf32 hi/lo operand tiles; rowptr / colidx / beta / gamma slices -> smem;
+//       GEMM1 (tcgen05) ; epilogue S' -> smem                              => csr_ready, sp_ready
+//   PE-B group (4 warps): waits for the workers' I_{k+1} operand tiles, GEMM2, epilogue, coalesced
+//       I'_{k+1} store                                                      => slot_free
+//   worker group (16 warps): per tile, row-per-half-warp: own-row loads + neighbour gather (up to 12
+//       row loads in flight per lane), SIR update, state stores, decoder, I_{k+1} hi/lo -> operand
+//       tiles                                                              => a2_ready
+// The groups meet only through mbarriers, so the gather/update stream of tile t overlaps the
+// GEMM/epilogue work of tiles t-1 and t+1; there is no block-wide barrier in the steady state.
+constexpr int WS_WORKERS = 512, WS_PE = 128, WS_THREADS = WS_WORKERS + 2 * WS_PE;   // workers | PE-A | PE-B
+constexpr int WS_CAP = 2816;
+constexpr int W_WHI = 0, W_WLO = 16384, W_SLOT = 32768, W_SLOT_BYTES = 65536;
+constexpr int W_CI = W_SLOT + 2 * W_SLOT_BYTES, W_CI_BYTES = WS_CAP * 4;
+constexpr int W_RP = W_CI + 2 * W_CI_BYTES, W_RP_BYTES = 544;
+constexpr int W_BG = W_RP + 2 * W_RP_BYTES, W_BG_BYTES = 2 * TILE * 4;
+constexpr int W_B = W_BG + 2 * W_BG_BYTES;
+constexpr int W_W3 = W_B + H * 4;
+constexpr int W_SMALL = W_W3 + 4 * H * 4;
+constexpr int W_BARS = W_SMALL + 64;          // 12 mbarriers (96 B), tmem slot, slot meta
+constexpr int W_TOTAL = W_BARS + 160 + 1024;
+static_assert(W_TOTAL <= 232448, "shared memory budget");
+enum { BAR_CSR = 0, BAR_SP = 2, BAR_A2 = 4, BAR_M1 = 6, BAR_M2 = 8, BAR_FREE = 10 };   // + slot
+
+// all lanes poll in lockstep (same issue cost as one lane, and no intra-warp divergence is introduced)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    (void)lane;
+    umma::mbar_wait(bar, parity);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(WS_THREADS, 1) step_ws_kernel(const StepArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* bs = reinterpret_cast<float*>(smem + W_B);
+    float* W3s = reinterpret_cast<float*>(smem + W_W3);
+    float* small = reinterpret_cast<float*>(smem + W_SMALL);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W_BARS);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + W_BARS + 96);
+    int* meta = reinterpret_cast<int*>(smem + W_BARS + 112);       // [slot][4]: tile, single
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index made provably warp-uniform, so that the role branches below are convergent for the compiler
+    // (otherwise every __shfl_sync inside them is compiled to the slow convergence-checking sequence)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    const int n_tiles = a.bv.n_tiles;
+
+    umma::prepare_weights(a.p.lin_w, smem + W_WHI, smem + W_WLO, tid, WS_THREADS);
+    if (warp == 0) umma::tmem_alloc(tslot, 256);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            umma::mbar_init(bars + BAR_CSR + s, 1);
+            umma::mbar_init(bars + BAR_SP + s, 1);
+            umma::mbar_init(bars + BAR_A2 + s, WS_WORKERS);
+            umma::mbar_init(bars + BAR_M1 + s, 1);
+            umma::mbar_init(bars + BAR_M2 + s, 1);
+            umma::mbar_init(bars + BAR_FREE + s, 1);
+        }
+    }
+    umma::fence_before_sync();
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
+    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+    if (tid == 0) small[8] = a.p.s2_b[0];
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t whi = umma::smem_u32(smem + W_WHI), wlo = umma::smem_u32(smem + W_WLO);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    long long tacc[3] = {0, 0, 0};
+    long long tprev = clock64();
+#define WS_TICK(i) if (a.tbuf) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
+
+    if (warp < WS_WORKERS / 32) {
+        // =============================== workers ===============================
+        const int l = tid & 15, hw = tid >> 4;
+        const int off0 = sw_off(hw, l);
+        const float* lane_base = a.ip_in + 4 * l;
+        for (int t = 0;; ++t) {
+            const int s = t & 1;
+            const uint32_t par = (uint32_t)(t >> 1) & 1u;
+            mbar_wait_warp(bars + BAR_CSR + s, par, lane);
+            WS_TICK(0)
+            const int tile = __shfl_sync(0xffffffffu, meta[4 * s], 0);
+            if (tile < 0) break;
+            const bool single = __shfl_sync(0xffffffffu, meta[4 * s + 1], 0) != 0;
+            unsigned char* Xs = smem + W_SLOT + s * W_SLOT_BYTES;
+            unsigned char* Ls = Xs + 32768;
+            const int* ci_s = reinterpret_cast<const int*>(smem + W_CI + s * W_CI_BYTES);
+            const int* rp_s = reinterpret_cast<const int*>(smem + W_RP + s * W_RP_BYTES);
+            const float* bg_s = reinterpret_cast<const float*>(smem + W_BG + s * W_BG_BYTES);
+            const int tile0 = tile * TILE;
+            const int nrows = min(TILE, M - tile0);
+            const int ebase = single ? rp_s[0] : 0;
+            int inst = a.bv.tile_inst[tile];
+            mbar_wait_warp(bars + BAR_SP + s, par, lane);      // S' of this tile (PE-A runs a tile ahead)
+            WS_TICK(2)
+#pragma unroll 1
+            for (int it = 0; it < TILE / 32; ++it) {
+                const int rr = hw + 32 * it;
+                const bool valid = rr < nrows;
+                const size_t off = (size_t)(tile0 + (valid ? rr : 0)) * H + 4 * l;
+                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), iv = sv, rv = sv, ipo = sv, acc = sv;
+                if (valid && !(a.dbg & 4)) {              // own rows: in flight during the gather
+                    sv = ldg4_hint(a.y_in + off, pol_stream);
+                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
+                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
+                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
+                }
+                if (single) {
+                    if (valid) {
+                        const int e_rel = rp_s[rr] - ebase, deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr];
+                        if (e_rel + deg <= WS_CAP) {
+                            acc = gather_smem(lane_base, ci_s + e_rel, deg, pol_keep);
+                        } else {                          // hub tile: indices beyond the staged slice
+                            const GnInstance I = a.bv.inst[inst];
+                            for (int j = 0; j < deg; ++j) {
+                                const int c = I.colidx[ebase + e_rel + j] + I.row0;
+                                const float4 v = ldg4_hint(lane_base + (size_t)c * H, pol_keep);
+                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {                                  // tile spans several (small) instances
+                    int row0 = 0, e0 = 0, deg = 0;
+                    const int32_t* ci = nullptr;
+                    if (valid) {
+                        const int g = tile0 + rr;
+                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                        const GnInstance I = a.bv.inst[inst];
+                        row0 = I.row0; ci = I.colidx;
+                        e0 = I.rowptr[g - row0];
+                        deg = I.rowptr[g - row0 + 1] - e0;
+                    }
+                    acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                }
+                float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
+                if (valid) {
+                    const float4 sp = lds4(Ls, off0 + it * 4096);
+                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
+#define GN_COMP(c)                                                                  \
+    {                                                                               \
+        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
+        const float dR = __fmul_rn(ga, ipo.c);                                      \
+        const float dI = __fsub_rn(-dS, dR);                                        \
+        sn.c = __fadd_rn(sv.c, __fmul_rn(dt, dS));                                  \
+        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
+        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
+    }
+                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+#undef GN_COMP
+                    stg4_hint(a.y_out + off, sn, pol_stream);
+                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
+                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
+                    float4 hi, lo;
+                    umma::tf32_split4(in_, hi, lo);          // operand of GEMM2
+                    sts4(Xs, off0 + it * 4096, hi);
+                    sts4(Ls, off0 + it * 4096, lo);
+                }
+                if (a.probs != nullptr && !(a.dbg & 1))
+                    decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
+            }
+            umma::fence_proxy_async();
+            umma::mbar_arrive(bars + BAR_A2 + s);
+            WS_TICK(1)
+        }
+        if (a.tbuf && tid == 0) for (int i = 0; i < 3; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
+    } else {
+        // =============================== PE groups ===============================
+        const bool group_b = warp >= (WS_WORKERS + WS_PE) / 32;
+        const int ptid = (tid - WS_WORKERS) & (WS_PE - 1), pwarp = ptid >> 5;
+        const int bar_id = group_b ? 2 : 1;
+        const int poff0 = sw_off(ptid >> 4, ptid & 15);           // chunk (ptid&15) of rows (ptid>>4) + 8*i: + i KB
+        auto epilogue = [&](uint32_t acc_addr, unsigned char* dst) {
+            const int row = pwarp * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[16];
+                umma::tmem_ld16(acc_addr + ((uint32_t)(pwarp * 32) << 16) + 16 * c, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
+                    float4 o;
+                    o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                    o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                    sts4(dst, sw_off(row, 4 * c + j), o);
+                }
+            }
+            umma::fence_before_sync();
+        };
+        if (!group_b) {
+            // -------- PE-A: operand preparation, GEMM1, S' epilogue
+            // The tile stream is fetched one tile ahead (meta[8..9]) so that the HBM -> L2 bulk prefetch of a
+            // tile's S / I / R / I' rows is issued a whole tile period before they are read.
+            auto fetch_next = [&](int k) {               // thread 0 only
+                const int seq = a.counter ? atomicAdd(a.counter, 1) : (int)blockIdx.x + k * (int)gridDim.x;
+                int tile = -1, single = 0;
+                if (seq < n_tiles) {
+                    tile = a.bv.tile_order[seq];
+                    const int t0 = tile * TILE, nr = min(TILE, M - t0);
+                    const GnInstance I = a.bv.inst[a.bv.tile_inst[tile]];
+                    single = (t0 + nr <= I.row0 + I.n) ? 1 : 0;
+                    if (!(a.dbg & 32)) {
+                        const uint32_t bytes = (uint32_t)nr * H * 4;
+                        prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
+                        prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
+                        prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
+                        prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
+                        const int ahead = t0 + I.n;     // same rows of the next instance (trial): I' for its gathers
+                        if (ahead < M) prefetch_l2_bulk_hint(a.ip_in + (size_t)ahead * H, (uint32_t)min(TILE, M - ahead) * H * 4, pol_keep);
+                    }
+                }
+                meta[8] = tile; meta[9] = single;
+            };
+            if (ptid == 0) fetch_next(0);
+            for (int k = 0;; ++k) {
+                const int s = k & 1;
+                const uint32_t par = (uint32_t)(k >> 1) & 1u;
+                unsigned char* Xs = smem + W_SLOT + s * W_SLOT_BYTES;
+                unsigned char* Ls = Xs + 32768;
+                int* ci_s = reinterpret_cast<int*>(smem + W_CI + s * W_CI_BYTES);
+                int* rp_s = reinterpret_cast<int*>(smem + W_RP + s * W_RP_BYTES);
+                float* bg_s = reinterpret_cast<float*>(smem + W_BG + s * W_BG_BYTES);
+                if (k >= 2) mbar_wait_warp(bars + BAR_FREE + s, par ^ 1u, lane);     // tile k-2 has left the slot
+                WS_TICK(0)
+                if (ptid == 0) { meta[4 * s] = meta[8]; meta[4 * s + 1] = meta[9]; }
+                umma::bar_sync(bar_id, WS_PE);
+                const int tile = __shfl_sync(0xffffffffu, meta[4 * s], 0);
+                if (tile < 0) {
+                    if (ptid == 0) umma::mbar_arrive(bars + BAR_CSR + s);
+                    break;
+                }
+                const bool single = __shfl_sync(0xffffffffu, meta[4 * s + 1], 0) != 0;
+                const int tile0 = tile * TILE, nrows = min(TILE, M - tile0);
+                const int inst0 = a.bv.tile_inst[tile];
+                const int i_row0 = a.bv.inst[inst0].row0;
+                const int32_t* rp = a.bv.inst[inst0].rowptr + (tile0 - i_row0);
+                // first wave of loads: CSR bounds, rowptr slice, beta/gamma, first half of the S rows
+                int e0 = 0, e1 = 0, rpv = 0, rp_last = 0;
+                float bev = 0.f, gav = 0.f;
+                if (single) {
+                    e0 = rp[0]; e1 = rp[nrows];
+                    if (ptid <= nrows) rpv = rp[ptid];
+                    if (ptid == 0 && nrows == TILE) rp_last = rp[TILE];
+                }
+                if (ptid < nrows) { bev = a.beta[tile0 + ptid]; gav = a.gamma[tile0 + ptid]; }
+                const float* src = a.y_in + (size_t)tile0 * H + (size_t)(ptid >> 4) * H + 4 * (ptid & 15);
+                float4 x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    x[i] = ((ptid >> 4) + 8 * i < nrows) ? ldg4(src + (size_t)(8 * i) * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ptid == 0) fetch_next(k + 1);        // atomic + prefetch issue overlap the loads above
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 hi, lo;
+                    umma::tf32_split4(x[i], hi, lo);
+                    sts4(Xs, poff0 + i * 1024, hi);
+                    sts4(Ls, poff0 + i * 1024, lo);
+                }
+                // second wave: second half of the S rows + the colidx slice (needs only e0 / e1)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    x[i] = ((ptid >> 4) + 8 * (8 + i) < nrows) ? ldg4(src + (size_t)(8 * (8 + i)) * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (single) {
+                    const int ecnt = min(e1 - e0, WS_CAP);
+                    const int32_t* cg = a.bv.inst[inst0].colidx + e0;
+                    for (int j0 = ptid; j0 < ecnt; j0 += 8 * WS_PE) {
+                        int c[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) c[u] = (j0 + u * WS_PE < ecnt) ? cg[j0 + u * WS_PE] : 0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (j0 + u * WS_PE < ecnt) ci_s[j0 + u * WS_PE] = c[u] + i_row0;
+                    }
+                    if (ptid <= nrows) rp_s[ptid] = rpv;
+                    if (ptid == 0 && nrows == TILE) rp_s[TILE] = rp_last;
+                }
+                if (ptid < nrows) { bg_s[ptid] = bev; bg_s[TILE + ptid] = gav; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 hi, lo;
+                    umma::tf32_split4(x[i], hi, lo);
+                    sts4(Xs, poff0 + (8 + i) * 1024, hi);
+                    sts4(Ls, poff0 + (8 + i) * 1024, lo);
+                }
+                umma::fence_proxy_async();
+                umma::bar_sync(bar_id, WS_PE);
+                if (ptid == 0)
+                    umma::issue_split_gemm_to(tmem + s * 64, bars + BAR_M1 + s, whi, wlo, umma::smem_u32(Xs), umma::smem_u32(Ls));
+                umma::bar_sync(bar_id, WS_PE);
+                if (ptid == 0) umma::mbar_arrive(bars + BAR_CSR + s);          // workers may start gathering
+                WS_TICK(1)
+                mbar_wait_warp(bars + BAR_M1 + s, par, lane);
+                umma::fence_after_sync();
+                epilogue(tmem + s * 64, Ls);
+                umma::bar_sync(bar_id, WS_PE);
+                if (ptid == 0) umma::mbar_arrive(bars + BAR_SP + s);           // S' ready
+                WS_TICK(2)
+            }
+            if (a.tbuf && ptid == 0) for (int i = 0; i < 3; ++i) atomicAdd((unsigned long long*)a.tbuf + 3 + i, (unsigned long long)tacc[i]);
+        } else {
+            // -------- PE-B: GEMM2, I' epilogue, store
+            for (int k = 0;; ++k) {
+                const int s = k & 1;
+                const uint32_t par = (uint32_t)(k >> 1) & 1u;
+                unsigned char* Xs = smem + W_SLOT + s * W_SLOT_BYTES;
+                unsigned char* Ls = Xs + 32768;
+                mbar_wait_warp(bars + BAR_CSR + s, par, lane);                 // tile id of this slot is published
+                const int tile = __shfl_sync(0xffffffffu, meta[4 * s], 0);
+                if (tile < 0) break;
+                const int tile0 = tile * TILE, nrows = min(TILE, M - tile0);
+                mbar_wait_warp(bars + BAR_A2 + s, par, lane);                  // I_{k+1} operand tiles complete
+                WS_TICK(0)
+                if (ptid == 0)
+                    umma::issue_split_gemm_to(tmem + 128 + s * 64, bars + BAR_M2 + s, whi, wlo, umma::smem_u32(Xs), umma::smem_u32(Ls));
+                mbar_wait_warp(bars + BAR_M2 + s, par, lane);
+                umma::fence_after_sync();
+                epilogue(tmem + 128 + s * 64, Ls);
+                umma::bar_sync(bar_id, WS_PE);
+                float* dst = a.ip_out + (size_t)tile0 * H + (size_t)(ptid >> 4) * H + 4 * (ptid & 15);
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i)
+                    if ((ptid >> 4) + 8 * i < nrows) stg4_hint(dst + (size_t)(8 * i) * H, lds4(Ls, poff0 + i * 1024), pol_stream);
+                umma::bar_sync(bar_id, WS_PE);
+                if (ptid == 0) umma::mbar_arrive(bars + BAR_FREE + s);         // slot may be refilled
+                WS_TICK(1)
+            }
+            if (a.tbuf && ptid == 0) for (int i = 0; i < 2; ++i) atomicAdd((unsigned long long*)a.tbuf + 6 + i, (unsigned long long)tacc[i]);
+        }
+    }
+#undef WS_TICK
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
 // 0 = FFMA + accurate sigmoid ... 3 = tcgen05 + MUFU sigmoid; chosen by gnode_set_variant() / GNODE_VARIANT
 static int g_variant = -1;
+static long long* g_tbuf = nullptr;      // phase-timing accumulators of step_tc_kernel (GNODE_DBG bit 7)
 
 static int current_variant() {
     if (g_variant < 0) {
@@ -609,10 +970,31 @@ static int launch_step_tc(const gnode_batch* b, const StepArgs& a, cudaStream_t 
     return GNODE_OK;
 }
 
+template <bool FAST>
+static int launch_step_ws(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(step_ws_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const int grid = std::min(b->n_tiles, b->sm_count);
+    step_ws_kernel<FAST><<<grid, WS_THREADS, W_TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
+static int step_kernel_choice() {     // 1 = phase-structured (default), 2 = warp-specialised, 0 = generic
+    static int c = -1;
+    if (c < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); c = e ? atoi(e) : 1; }
+    return c;
+}
+
 template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
-    if (MODE == MODE_STEP && (var & VAR_TC) && !getenv("GNODE_GENERIC_STEP"))
+    if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 2)
+        return (var & VAR_FASTSIG) ? launch_step_ws<true>(b, a, stream) : launch_step_ws<false>(b, a, stream);
+    if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 1)
         return (var & VAR_FASTSIG) ? launch_step_tc<true>(b, a, stream) : launch_step_tc<false>(b, a, stream);
     switch (var) {
         case 0: return launch_step_v<MODE, 0>(b, a, stream);
@@ -634,6 +1016,16 @@ extern "C" int gnode_set_variant(int variant) {
     return GNODE_OK;
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
+extern "C" int gnode_debug_phase_cycles(long long* out8) {
+    if (!out8) return GNODE_ERR_ARG;
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (!g_tbuf) return GNODE_OK;
+    GN_CUDA(cudaDeviceSynchronize());
+    GN_CUDA(cudaMemcpy(out8, g_tbuf, 64, cudaMemcpyDeviceToHost));
+    GN_CUDA(cudaMemset(g_tbuf, 0, 64));
+    return GNODE_OK;
+}
+
 
 extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) {
     if (!b) return 0;
@@ -683,6 +1075,11 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     a.y_out = state(0); a.ip_out = ip[0];
     a.probs = probs; a.dt = 0.f;
     a.dbg = getenv("GNODE_DBG") ? atoi(getenv("GNODE_DBG")) : 0;
+    a.tbuf = nullptr;
+    if (a.dbg & 128) {
+        if (!g_tbuf) { GN_CUDA(cudaMalloc(&g_tbuf, 64)); GN_CUDA(cudaMemset(g_tbuf, 0, 64)); }
+        a.tbuf = g_tbuf;
+    }
     a.counter = (a.dbg & 64) ? nullptr : counters;
     int rc = launch_step<MODE_ENCODE>(b, a, stream);
     if (rc) return rc;
@@ -709,7 +1106,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;

@@ -46,6 +46,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout)
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 [0,14) | LBO>>4 [16,30) (ignored for
 // swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups | version=1 [46,48) | layout=2 [61,64)
@@ -119,6 +127,26 @@ __device__ __forceinline__ void prepare_weights(const float* __restrict__ W, uns
 
 // One thread: D[128x64] = Xlo Wlo^T + Xlo Whi^T + Xhi Wlo^T + Xhi Whi^T (small terms first), then commit.
 // 4 passes x 8 K-steps of tcgen05.mma kind::tf32 (M128 N64 K8).
+__device__ __forceinline__ void issue_split_gemm_to(uint32_t tmem, uint64_t* bar, uint32_t whi, uint32_t wlo,
+                                                    uint32_t xhi, uint32_t xlo) {
+    fence_after_sync();
+    constexpr uint32_t idesc = instr_desc_tf32(TILE, H);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const uint32_t abase = (pass < 2) ? xlo : xhi;
+        const uint32_t bbase = (pass == 0 || pass == 2) ? wlo : whi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
+            const uint32_t boff = ((k >> 2) << 13) + ((k & 3) << 5);
+            mma_tf32(tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
+            acc = 1;
+        }
+    }
+    mma_commit(bar);
+}
+
 __device__ __forceinline__ void issue_split_gemm(const Ctx& cx, uint32_t xhi, uint32_t xlo) {
     fence_after_sync();
     constexpr uint32_t idesc = instr_desc_tf32(TILE, H);
@@ -142,8 +170,7 @@ __device__ __forceinline__ void issue_split_gemm(const Ctx& cx, uint32_t xhi, ui
 // block: dst = sigmoid(acc + b) written thread-per-row into the swizzled tile dst.
 template <bool FAST>
 __device__ __forceinline__ void epilogue_sigmoid(Ctx& cx, unsigned char* dst, const float* bs, int warp, int lane) {
-    if (lane == 0) mbar_wait(cx.bar, cx.phase);          // one poller per warp
-    __syncwarp();
+    mbar_wait(cx.bar, cx.phase);
     fence_after_sync();
     const int q = warp & 3, cq = warp >> 2;
     float v[16];

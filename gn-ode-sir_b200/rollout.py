@@ -42,7 +42,7 @@ def dt_array(integration_time):
 
 class _Rollout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, batch, dt, grad_mode, *params):
+    def forward(ctx, x, batch, dt, grad_mode, want_grad, *params):
         L = _lib.lib()
         M, T = batch.M, len(dt) + 1
         _check_cuda_f32(x, "x")
@@ -52,7 +52,8 @@ class _Rollout(torch.autograd.Function):
         for k, p in zip(PARAM_ORDER, params):
             _check_cuda_f32(p, k)
             ps.append(p.detach().contiguous())
-        need_grad = any(ctx.needs_input_grad[4:])
+        # grad mode is always off inside forward(): the caller's grad mode arrives as `want_grad`
+        need_grad = bool(want_grad) and any(ctx.needs_input_grad[5:])
         traj = torch.empty((T, 3, M, H), dtype=torch.float32, device=x.device) if need_grad else None
         probs = torch.empty((T, M, 3), dtype=torch.float32, device=x.device)
         ws_bytes = int(L.gnode_rollout_workspace_bytes(batch.handle, 1 if need_grad else 0))
@@ -86,16 +87,17 @@ class _Rollout(torch.autograd.Function):
         out, off = [], 0
         for i, (k, shape) in enumerate(_lib.GRAD_LAYOUT):
             n = int(np.prod(shape))
-            out.append(grads[off:off + n].view(shape) if ctx.needs_input_grad[4 + i] else None)
+            out.append(grads[off:off + n].view(shape) if ctx.needs_input_grad[5 + i] else None)
             off += n
-        return (None, None, None, None, *out)
+        return (None, None, None, None, None, *out)
 
 
 def rollout(x, batch, dt, params, grad_mode="adjoint"):
     """x [M, >=5] -> probabilities [T, M, 3]; params in PARAM_ORDER (state_dict names)."""
     if grad_mode not in ("adjoint", "discrete"):
         raise ValueError("grad_mode must be 'adjoint' or 'discrete'")
-    return _Rollout.apply(x, batch, dt, grad_mode, *params)
+    want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _Rollout.apply(x, batch, dt, grad_mode, want_grad, *params)
 
 
 def odefunc_eval(y, beta, gamma, batch, params):

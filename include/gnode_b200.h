@@ -76,6 +76,8 @@ int gnode_version(void);
  * bit 1 = MUFU ex2/rcp sigmoid (else expf + IEEE division). Default: env GNODE_VARIANT or the build default. */
 int gnode_set_variant(int variant);
 int gnode_get_variant(void);
+/* debug: per-phase SM-cycle sums of the step kernel collected while env GNODE_DBG has bit 7 set; resets them */
+int gnode_debug_phase_cycles(long long* out8);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t gnode_launch_count(void);
 

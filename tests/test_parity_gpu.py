@@ -3,7 +3,9 @@
   (2) the CPU oracle on freshly seeded inputs.
 Tolerances (fp32 path; BASELINE.json north_star: 1e-5 max-abs on probabilities):
   * aggregation            bit-exact (same ascending-column sequential fp32 sum as the CPU reference)
-  * one rhs evaluation     2e-6 * max|f| scale-relative (teacher-forced on oracle states)
+  * one rhs evaluation     6e-6 * max|f| scale-relative, teacher-forced on oracle states (SURVEY H1.ii);
+                           the default kernel variant computes S W^T as a 4-term tf32 split on tcgen05
+                           (per-product error 2^-22); the fp32 FFMA variant meets 2e-6 (test_variants_gpu.py)
   * probabilities, small   1e-5 max-abs vs the reference fp32 outputs
   * probabilities, large   err(ours, fp64) <= max(1e-5, 2 * err(ref_fp32, fp64))
 """
@@ -88,7 +90,7 @@ def test_rhs_teacher_forced(gn, name, k):
     got = gn.rollout.odefunc_eval(y.to(DEV), beta.to(DEV), gamma.to(DEV), batch,
                                   [W.to(DEV), b.to(DEV)] + [b.to(DEV)] * 6).cpu()
     scale = want.abs().max().item()
-    assert (got - want).abs().max().item() <= 2e-6 * scale + 1e-30, ((got - want).abs().max().item(), scale)
+    assert (got - want).abs().max().item() <= 6e-6 * scale + 1e-30, ((got - want).abs().max().item(), scale)
     # conservation: dS + dI + dR == 0 up to rounding of the last subtraction
     assert (got.sum(0)).abs().max().item() <= 1e-6 * scale
 
@@ -231,4 +233,4 @@ def test_dropin_modules_forward(gn, name):
         assert out.shape == (4, g.M, g.H)
         got, tail = out[:3], out[3]
     assert float(tail.abs().max()) == 0.0
-    assert (got - want).abs().max().item() <= 2e-6 * want.abs().max().item()
+    assert (got - want).abs().max().item() <= 6e-6 * want.abs().max().item()
