@@ -74,6 +74,7 @@ struct gnode_batch {
     GnInstance* d_inst = nullptr;    // [n_inst]
     int32_t* d_tile_inst = nullptr;  // [n_tiles] instance that owns the first row of each tile
     int32_t* d_tile_order = nullptr; // [n_tiles] processing order: hub-heavy tiles first, then row-major
+    int2* d_sched = nullptr;         // [n_tiles] by sequence number: {tile, first row of the look-ahead I' prefetch or -1}
     int device = 0;
     int sm_count = 0;
 };
@@ -83,6 +84,7 @@ struct GnBatchView {
     const GnInstance* inst;
     const int32_t* tile_inst;
     const int32_t* tile_order;
+    const int2* sched;
     int32_t n_inst;
     int32_t n_tiles;
     int32_t M;
@@ -93,6 +95,7 @@ inline GnBatchView gn_view(const gnode_batch* b) {
     v.inst = b->d_inst;
     v.tile_inst = b->d_tile_inst;
     v.tile_order = b->d_tile_order;
+    v.sched = b->d_sched;
     v.n_inst = b->n_inst;
     v.n_tiles = b->n_tiles;
     v.M = (int32_t)b->M;

@@ -290,7 +290,7 @@ constexpr int T_B = T_WLO + H * H * 4;          // bias [64]
 constexpr int T_W3 = T_B + H * 4;               // linear3.weight [4][64]
 constexpr int T_SMALL = T_W3 + 4 * H * 4;       // b3[4], w2[4], b2
 constexpr int T_MBAR = T_SMALL + 64;            // mbarrier (8) + tmem slot (4) + next-tile slot (4)
-constexpr int T_BG = T_MBAR + 16;               // beta[TILE], gamma[TILE] of the tile
+constexpr int T_BG = T_MBAR + 32;               // beta[TILE], gamma[TILE] of the tile
 constexpr int T_RP = T_BG + 2 * TILE * 4;       // rowptr slice [TILE + 1] (+pad)
 constexpr int T_CI = T_RP + 544;                // colidx slice [CSR_CAP] as global row ids
 constexpr int T_TOTAL = T_CI + CSR_CAP * 4 + 1024;
@@ -374,6 +374,36 @@ __device__ __forceinline__ float4 gather_smem(const float* __restrict__ lane_bas
     return acc;
 }
 
+// Warp-uniform variant: both half-warps of the warp (two adjacent rows) run the same trip counts
+// (bounded by the larger degree, loads predicated per row), so the warp never diverges; rows with up to
+// 11 neighbours complete in ONE memory round trip (8 + 3 loads in flight per lane).
+__device__ __forceinline__ float4 gather_smem_uniform(const float* __restrict__ lane_base, const int* cp, int deg, uint64_t pol) {
+    const int degm = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; degm - j > 11; j += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j + k < deg) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+    {
+        float4 v[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j + k < deg) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
+        }
+#pragma unroll
+        for (int k = 0; k < 11; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+    return acc;
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) {
     extern __shared__ unsigned char smem_raw[];
@@ -386,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T_MBAR);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + T_MBAR + 8);
     int* seq_slot = reinterpret_cast<int*>(smem + T_MBAR + 12);
+    int* row_ctr = reinterpret_cast<int*>(smem + T_MBAR + 16);
     float* bg_s = reinterpret_cast<float*>(smem + T_BG);
     int* rp_s = reinterpret_cast<int*>(smem + T_RP);
     int* ci_s = reinterpret_cast<int*>(smem + T_CI);
@@ -418,26 +449,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
     const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
 
     int seq = *seq_slot;
-    // HBM -> L2 one tile ahead: the S tile (operand of GEMM1) and the own-row operands of the row phases
-    auto prefetch_tile = [&](int sq) {
-        if (sq < n_tiles && tid == 0 && !(a.dbg & 32)) {
-            const int t0 = a.bv.tile_order[sq] * TILE;
-            const uint32_t bytes = (uint32_t)min(TILE, M - t0) * H * 4;
-            prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
-            prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
-            prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
-            prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
-            // look-ahead: the same rows of the NEXT instance (trial), so that its gathers find I' in L2
-            const int ahead = t0 + a.bv.inst[a.bv.tile_inst[a.bv.tile_order[sq]]].n;
-            if (ahead < M) prefetch_l2_bulk_hint(a.ip_in + (size_t)ahead * H, (uint32_t)min(TILE, M - ahead) * H * 4, pol_keep);
-        }
+    // HBM -> L2 one tile ahead: the S tile (operand of GEMM1), the own-row operands of the row phases, and the
+    // I' rows of the same tile one instance (trial) ahead, kept in L2 for that instance's gathers
+    auto prefetch_rows = [&](int2 sc) {            // thread 0; sc = schedule entry {tile, look-ahead row}
+        if (a.dbg & 32) return;
+        const int t0 = sc.x * TILE;
+        const uint32_t bytes = (uint32_t)min(TILE, M - t0) * H * 4;
+        prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
+        prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
+        prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
+        prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
+        if (sc.y >= 0) prefetch_l2_bulk_hint(a.ip_in + (size_t)sc.y * H, (uint32_t)min(TILE, M - sc.y) * H * 4, pol_keep);
     };
-    prefetch_tile(seq);
+    if (tid == 0 && seq < n_tiles) prefetch_rows(a.bv.sched[seq]);
 
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
 #define GN_TICK(i) if (a.tbuf && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
     while (seq < n_tiles) {
+        // next tile of this CTA: the atomic is issued now, its result is first used after the gather phase
+        int nseq = 0;
+        if (tid == 0) nseq = a.counter ? atomicAdd(a.counter, 1) : seq + (int)gridDim.x;
         const int tile = a.bv.tile_order[seq];
         const int tile0 = tile * TILE;
         const int nrows = min(TILE, M - tile0);
@@ -462,7 +494,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
             }
         }
         umma::fence_proxy_async();
-        if (single && tid <= nrows) rp_s[tid] = a.bv.inst[inst0].rowptr[tile0 - i_row0 + tid];
+        if (tid == 0) *row_ctr = 0;
+        if (single && tid <= nrows) rp_s[tid] = __ldg(a.bv.inst[inst0].rowptr + (tile0 - i_row0 + tid));
         if (tid >= 256 && tid < 256 + nrows) bg_s[tid - 256] = a.beta[tile0 + tid - 256];
         if (tid >= 384 && tid < 384 + nrows) bg_s[TILE + tid - 384] = a.gamma[tile0 + tid - 384];
         __syncthreads();                                                        // S1
@@ -478,33 +511,42 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
         if (!(a.dbg & 16)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
         __syncthreads();                                                        // S2
         GN_TICK(1)
-        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile
+        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile. Row pairs are handed out
+        //      dynamically (shared-memory counter) so that hub rows do not leave the other warps idle.
         {
             const float* lane_base = a.ip_in + 4 * l;
-            int inst = inst0;
-#pragma unroll 1
-            for (int it = 0; it < TILE / 32; ++it) {
-                const int rr = hw + 32 * it;
-                const bool valid = rr < nrows;
-                float4 acc;
-                if (single) {
-                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) {
-                        const int e_rel = rp_s[rr] - ebase, deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr];
-                        if (e_rel + deg <= CSR_CAP) {
-                            acc = gather_smem(lane_base, ci_s + e_rel, deg, pol_keep);
-                        } else {                             // hub tile: indices beyond the staged slice
-                            for (int j = 0; j < deg; ++j) {
-                                const int c = i_colidx[ebase + e_rel + j] + i_row0;
-                                const float4 v = ldg4_hint(lane_base + (size_t)c * H, pol_keep);
-                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                            }
+            if (single) {
+                for (;;) {
+                    int p = 0;
+                    if (lane == 0) p = atomicAdd(row_ctr, 1);
+                    p = __shfl_sync(0xffffffffu, p, 0);
+                    if (p >= TILE / 2) break;
+                    const int rr = 2 * p + (lane >> 4);
+                    int e_rel = 0, deg = 0;
+                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
+                    const int over = (e_rel + deg > CSR_CAP) ? 1 : 0;
+                    float4 acc;
+                    if (__any_sync(0xffffffffu, over)) {         // hub tile: indices beyond the staged slice
+                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < deg; ++j) {
+                            const int c = i_colidx[ebase + e_rel + j] + i_row0;
+                            const float4 v = ldg4_hint(lane_base + (size_t)c * H, pol_keep);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                         }
+                        __syncwarp();
+                    } else {
+                        acc = gather_smem_uniform(lane_base, ci_s + e_rel, deg, pol_keep);
                     }
-                } else {                                     // tile spans several (small) instances
+                    sts4(Xs, sw_off(rr, l), acc);
+                }
+            } else {                                         // tile spans several (small) instances
+                int inst = inst0;
+#pragma unroll 1
+                for (int it = 0; it < TILE / 32; ++it) {
+                    const int rr = hw + 32 * it;
                     int row0 = 0, e0 = 0, deg = 0;
                     const int32_t* ci = nullptr;
-                    if (valid) {
+                    if (rr < nrows) {
                         const int g = tile0 + rr;
                         while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
                         const GnInstance I = a.bv.inst[inst];
@@ -512,31 +554,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
                         e0 = I.rowptr[g - row0];
                         deg = I.rowptr[g - row0 + 1] - e0;
                     }
-                    acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                    const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                    sts4(Xs, off0 + it * 4096, acc);
                 }
-                sts4(Xs, off0 + it * 4096, acc);
             }
         }
-        __syncwarp();
+        __syncthreads();                                                        // S2b: every AI row is parked
         GN_TICK(2)
-        // ---- P3b: SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles
-#pragma unroll 1
-        for (int it = 0; it < TILE / 32; ++it) {
-            const int rr = hw + 32 * it;
-            const bool valid = rr < nrows;
-            const size_t off = (size_t)(tile0 + (valid ? rr : 0)) * H + 4 * l;
-            float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
-            if (valid) {
-                float4 s = make_float4(1.f, 1.f, 1.f, 1.f), iv = s, rv = s, ipo = s;
-                if (!(a.dbg & 4)) {
+        int2 nsched = make_int2(0, -1);
+        if (tid == 0) {
+            *seq_slot = nseq;
+            if (nseq < n_tiles) nsched = a.bv.sched[nseq];
+        }
+        // ---- P3b: SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles. The own-row loads of row
+        //      it+1 are issued before the decoder of row it, so their L2 latency hides behind its arithmetic.
+        {
+            float4 s, iv, rv, ipo;
+            auto load_own = [&](int it) {
+                const int rr = hw + 32 * it;
+                s = make_float4(1.f, 1.f, 1.f, 1.f); iv = s; rv = s; ipo = s;
+                if (rr < nrows && !(a.dbg & 4)) {
+                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
                     s = ldg4_hint(a.y_in + off, pol_stream);
                     iv = ldg4_hint(a.y_in + plane + off, pol_stream);
                     rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
                     ipo = ldg4_hint(a.ip_in + off, pol_keep);
                 }
-                const float4 acc = lds4(Xs, off0 + it * 4096);
-                const float4 sp = lds4(Ls, off0 + it * 4096);
-                const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
+            };
+            load_own(0);
+#pragma unroll 1
+            for (int it = 0; it < TILE / 32; ++it) {
+                const int rr = hw + 32 * it;
+                const bool valid = rr < nrows;
+                const size_t off = (size_t)(tile0 + (valid ? rr : 0)) * H + 4 * l;
+                float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
+                if (valid) {
+                    const float4 acc = lds4(Xs, off0 + it * 4096);
+                    const float4 sp = lds4(Ls, off0 + it * 4096);
+                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
 #define GN_COMP(c)                                                                  \
     {                                                                               \
         const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
@@ -546,28 +601,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
         in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
         rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
     }
-                GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
 #undef GN_COMP
-                stg4_hint(a.y_out + off, sn, pol_stream);
-                stg4_hint(a.y_out + plane + off, in_, pol_stream);
-                stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
-                float4 hi, lo;
-                umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
-                sts4(Xs, off0 + it * 4096, hi);
-                sts4(Ls, off0 + it * 4096, lo);
+                    stg4_hint(a.y_out + off, sn, pol_stream);
+                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
+                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
+                    float4 hi, lo;
+                    umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
+                    sts4(Xs, off0 + it * 4096, hi);
+                    sts4(Ls, off0 + it * 4096, lo);
+                }
+                if (it + 1 < TILE / 32) load_own(it + 1);
+                if (a.probs != nullptr && !(a.dbg & 1))
+                    decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
             }
-            if (a.probs != nullptr && !(a.dbg & 1))
-                decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
         }
         GN_TICK(3)
-        if (tid == 0) *seq_slot = a.counter ? atomicAdd(a.counter, 1) : seq + (int)gridDim.x;
         umma::fence_proxy_async();
         __syncthreads();                                                        // S3
         GN_TICK(4)
         // ---- P4: GEMM2 || prefetch of the next tile ; I' epilogue
         if (!(a.dbg & 8) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
         const int seq_next = *seq_slot;
-        prefetch_tile(seq_next);
+        if (tid == 0 && seq_next < n_tiles) prefetch_rows(nsched);
         if (!(a.dbg & 8)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
         __syncthreads();                                                        // S4
         GN_TICK(5)

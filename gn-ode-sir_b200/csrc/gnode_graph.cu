@@ -200,6 +200,17 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
     GN_CUDA(cudaMemcpy(b->d_inst, inst.data(), sizeof(GnInstance) * n_inst, cudaMemcpyHostToDevice));
     GN_CUDA(cudaMemcpy(b->d_tile_inst, tile_inst.data(), sizeof(int32_t) * b->n_tiles, cudaMemcpyHostToDevice));
     GN_CUDA(cudaMemcpy(b->d_tile_order, order.data(), sizeof(int32_t) * b->n_tiles, cudaMemcpyHostToDevice));
+    {   // schedule entries: tile + the row where the same tile of the NEXT instance starts (I' look-ahead prefetch)
+        std::vector<int2> sched(b->n_tiles);
+        for (int32_t q = 0; q < b->n_tiles; ++q) {
+            const int32_t t = order[q];
+            const int64_t ahead = (int64_t)t * TILE + inst[tile_inst[t]].n;
+            sched[q].x = t;
+            sched[q].y = ahead < M ? (int32_t)ahead : -1;
+        }
+        GN_CUDA(cudaMalloc(&b->d_sched, sizeof(int2) * b->n_tiles));
+        GN_CUDA(cudaMemcpy(b->d_sched, sched.data(), sizeof(int2) * b->n_tiles, cudaMemcpyHostToDevice));
+    }
     *out = b;
     return GNODE_OK;
 }
@@ -209,6 +220,7 @@ extern "C" int gnode_batch_destroy(gnode_batch_t b) {
     cudaFree(b->d_inst);
     cudaFree(b->d_tile_inst);
     cudaFree(b->d_tile_order);
+    cudaFree(b->d_sched);
     delete b;
     return GNODE_OK;
 }
