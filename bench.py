@@ -45,12 +45,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per step-kernel launch from the committed ncu --set full capture (or None)."""
+def ncu_traffic_per_launch(rows):
+    """DRAM bytes per step-kernel launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    `ncu --set full` capture (profiles/step_kernel_traffic.json holds bytes per row of that capture)."""
     p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(p):
         with open(p) as fh:
-            return json.load(fh)
+            return float(json.load(fh)["dram_bytes_per_row"]) * rows
     return None
 
 
@@ -260,10 +261,10 @@ def main():
     step_ms = ev[0].elapsed_time(ev[1]) / step_launches
     peak, peak_src = measured_peak()
     achieved = rows * ALGO_BYTES_PER_NODE_STEP / (step_ms * 1e-3) / 1e9
-    traffic = ncu_traffic_per_launch()
+    traffic = ncu_traffic_per_launch(rows)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                "kernel": "gnode::step_kernel<MODE_STEP>", "launch_ms": step_ms, "rows_per_launch": rows,
+                "traffic": traffic,
+                "kernel": "gnode::step_tc_kernel (fused Euler step, tcgen05)", "launch_ms": step_ms, "rows_per_launch": rows,
                 "algorithmic_bytes_per_node_step": ALGO_BYTES_PER_NODE_STEP, "peak_source": peak_src}
     del S, I, R
 
