@@ -37,7 +37,8 @@ struct StepArgs {
     float* gamma;         // [M]
     const float* x;       // ENCODE: [M][ldx]
     int64_t ldx;
-    float* probs;         // [M][3] slice of the produced state, or null
+    float* probs;         // [M][3] slice of the produced state (dual kernel: of the INPUT state), or null
+    float* hid_i;         // [M][4] linear3 pre-activations (no bias) of the I block: ENCODE writes I_0's, the dual step kernel updates in place; or null
     float dt;
     long long* tbuf;      // phase timing accumulators (debug, env GNODE_DBG bit 7) or null
     int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
@@ -64,7 +65,7 @@ constexpr int VAR_TC = 1, VAR_FASTSIG = 2;
 // decoder + softmax of one row held 4 channels per lane by a half-warp
 // (linear3 -> ReLU -> linearS2 -> softmax over {S,I,R}; ode_nn_ngraph_sim.py:172-187)
 __device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const float* W3s, const float* small,
-                                           int l, bool valid, float* probs_row) {
+                                           int l, bool valid, float* probs_row, float* hid_i_row = nullptr) {
     float v[12];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -75,7 +76,8 @@ __device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const f
     for (int off = 8; off >= 1; off >>= 1)
 #pragma unroll
         for (int m = 0; m < 12; ++m) v[m] += __shfl_xor_sync(0xffffffffu, v[m], off);
-    if (l == 0 && valid) {
+    if (l == 0 && valid && hid_i_row != nullptr) *reinterpret_cast<float4*>(hid_i_row) = make_float4(v[4], v[5], v[6], v[7]);
+    if (l == 0 && valid && probs_row != nullptr) {
         const float* b3 = small; const float* w2 = small + 4; const float b2 = small[8];
         float o[3];
 #pragma unroll
@@ -246,8 +248,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
                     stg4_stream(a.y_out + 2 * plane + off, r0);
                 }
                 sts4(Xs, sw_off(rr, l), i0);
-                if (a.probs != nullptr)
-                    decode_row(s0, i0, r0, W3s, small, l, valid, a.probs + (size_t)(valid ? g : 0) * 3);
+                if (a.probs != nullptr || a.hid_i != nullptr)
+                    decode_row(s0, i0, r0, W3s, small, l, valid, a.probs ? a.probs + (size_t)(valid ? g : 0) * 3 : nullptr,
+                               a.hid_i ? a.hid_i + (size_t)(valid ? g : 0) * 4 : nullptr);
             }
             __syncthreads();
         }
@@ -648,6 +651,565 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
 
 
 // ---------------------------------------------------------------------------------------------
+// Fused Euler step, "dual" kernel (the production kernel for MODE_STEP).
+//
+// ONE CTA of 1024 threads per SM = two independent 512-thread halves, each running the phase pipeline of
+// step_tc_kernel on its own tiles (own operand tiles, CSR slice, mbarrier, TMEM accumulator, named barrier),
+// while the W operand tiles, bias and decoder constants are shared. The shared-memory saved by not duplicating
+// W pays for the N = 80 operand [W; W3]: the decoder's hidden layer (linear3, ode_nn_ngraph_sim.py:172-176) of
+// the S and I blocks comes out of the two GEMMs that the step needs anyway, in accumulator columns 64..67:
+//   GEMM1: S_k     [W; W3]^T -> S'_k         and hid(S_k)
+//   GEMM2: I_{k+1} [W; W3]^T -> I'_{k+1}     and hid(I_{k+1})  -> HBM side buffer hid_i (16 B / row), read by step k+1
+//   hid(R_k): 16 FMAs + a 5-shuffle butterfly per lane in the update phase (R has no GEMM)
+// so the launch of step k emits probs[k] (the softmax of its INPUT state, one thread per row) instead of probs[k+1];
+// the host decodes the last state with decode_kernel. Differences from step_tc_kernel besides that:
+//   * the tcgen05.commit mbarrier is awaited with a suspend-time hint (the hardware parks the warps; no spin loop);
+//   * the gather and the update are one row phase: a row's own-row loads and its neighbour loads are in flight
+//     together, and the gather is specialised by ceil(deg / 4) (no 11-wide predicated tail).
+constexpr int D_THREADS = 1024, D_HALF = 512;
+constexpr int D_CAP = 1536;                               // colidx entries staged per tile (total smem <= 192 KB keeps >= 64 KB of L1)
+constexpr int D_WHI = 0;
+constexpr int D_WLO = umma::WB80_BYTES;
+constexpr int D_B = 2 * umma::WB80_BYTES;                 // bias [64]
+constexpr int D_W3 = D_B + H * 4;                         // linear3.weight [4][64] fp32 (hidden of R by FFMA)
+constexpr int D_SMALL = D_W3 + 4 * H * 4;                 // b3[4], w2[4], b2
+constexpr int D_TSLOT = D_SMALL + 64;                     // TMEM base slot
+constexpr int D_SHARED = 43008;                           // shared part, rounded up to 1 KB (operand tiles need 1024-B alignment)
+static_assert(D_TSLOT + 16 <= D_SHARED, "shared part overflows");
+constexpr int DH_X = 0;                                   // 32 KB  A operand hi / parked neighbour sums
+constexpr int DH_L = 32768;                               // 32 KB  A operand lo / S' / I' staging
+constexpr int DH_MBAR = 65536;                            // mbarrier (8) + sequence slot (4) + row-pair counter (4)
+constexpr int DH_BG = DH_MBAR + 32;                       // beta[TILE], gamma[TILE]
+constexpr int DH_RP = DH_BG + 2 * TILE * 4;               // rowptr slice [TILE + 1] (+pad)
+constexpr int DH_HS = DH_RP + 544;                        // hid(S_k) [TILE][4]
+constexpr int DH_HR = DH_HS + TILE * 16;                  // hid(R_k) [TILE][4]
+constexpr int DH_CI = DH_HR + TILE * 16;                  // colidx slice as global row ids
+constexpr int DH_BYTES = ((DH_CI + D_CAP * 4 + 1023) / 1024) * 1024;
+constexpr int D_TOTAL = D_SHARED + 2 * DH_BYTES + 1024;
+static_assert(D_TOTAL + 1024 <= 232448, "the CTA must fit in one SM's shared memory");
+
+// up to 4*NB neighbour rows of one row, all loads issued before the first add (one memory round trip)
+template <int NB>
+__device__ __forceinline__ void gather_block(float4& acc, const float* __restrict__ lane_base, const int* cp, int j0, int deg, uint64_t pol) {
+    float4 v[4 * NB];
+#pragma unroll
+    for (int k = 0; k < 4 * NB; ++k) {
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + k < deg) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j0 + k] * H, pol);
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * NB; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+}
+
+// Warp-uniform neighbour sum (both half-warps run the trip counts of the larger degree, loads predicated per row);
+// sequential ascending-column accumulation; rows with up to 12 neighbours complete in one round trip.
+template <int MAXB>       // MAXB = 3: up to 12 rows per round trip, 2: up to 8 (leaves registers for the own-row loads)
+__device__ __forceinline__ float4 gather_smem_nb(const float* __restrict__ lane_base, const int* cp, int deg, uint64_t pol) {
+    const int degm = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; degm - j > 4 * MAXB; j += 8) gather_block<2>(acc, lane_base, cp, j, deg, pol);
+    const int rem = degm - j;
+    if (MAXB >= 3 && rem > 8) gather_block<3>(acc, lane_base, cp, j, deg, pol);
+    else if (rem > 4) gather_block<2>(acc, lane_base, cp, j, deg, pol);
+    else if (rem > 0) gather_block<1>(acc, lane_base, cp, j, deg, pol);
+    return acc;
+}
+
+// K neighbour rows, no predication: slots past the row's degree read the all-zero row `zrow` of the I' buffer
+// (adding +0 is exact), so the loads need neither a zero-initialised destination nor a predicate.
+template <int K>
+__device__ __forceinline__ void gather_exact(float4& acc, const float* __restrict__ lane_base, const int* cp, int j0, int deg, int zrow, uint64_t pol) {
+    float4 v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = (j0 + k < deg) ? cp[j0 + k] : zrow;
+        v[k] = ldg4_hint(lane_base + (size_t)(unsigned)c * H, pol);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+}
+
+// Warp-uniform neighbour sum specialised by the pair's larger degree (1..12 in one round trip, longer rows in
+// rounds of 8); sequential ascending-column accumulation per row.
+__device__ __forceinline__ float4 gather_smem_z(const float* __restrict__ lane_base, const int* cp, int deg, int zrow, uint64_t pol) {
+    const int degm = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; degm - j > 12; j += 8) gather_exact<8>(acc, lane_base, cp, j, deg, zrow, pol);
+    switch (degm - j) {
+        case 12: gather_exact<12>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 11: gather_exact<11>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 10: gather_exact<10>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 9: gather_exact<9>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 8: gather_exact<8>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 7: gather_exact<7>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 6: gather_exact<6>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 5: gather_exact<5>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 4: gather_exact<4>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 3: gather_exact<3>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 2: gather_exact<2>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 1: gather_exact<1>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        default: break;
+    }
+    return acc;
+}
+
+template <bool FAST, bool FUSED>
+__global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x;
+    const int half = __shfl_sync(0xffffffffu, tid >> 9, 0);          // provably warp-uniform
+    const int t = tid & (D_HALF - 1), lane = t & 31;
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);            // warp index inside the half
+    const int l = t & 15, hw = t >> 4;
+    unsigned char* hb = smem + D_SHARED + half * DH_BYTES;
+    unsigned char* Xs = hb + DH_X;
+    unsigned char* Ls = hb + DH_L;
+    float* bs = reinterpret_cast<float*>(smem + D_B);
+    float* W3s = reinterpret_cast<float*>(smem + D_W3);
+    float* small = reinterpret_cast<float*>(smem + D_SMALL);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + D_TSLOT);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(hb + DH_MBAR);
+    int* seq_slot = reinterpret_cast<int*>(hb + DH_MBAR + 8);
+    int* row_ctr = reinterpret_cast<int*>(hb + DH_MBAR + 12);
+    float* bg_s = reinterpret_cast<float*>(hb + DH_BG);
+    int* rp_s = reinterpret_cast<int*>(hb + DH_RP);
+    float* hs_s = reinterpret_cast<float*>(hb + DH_HS);
+    float* hr_s = reinterpret_cast<float*>(hb + DH_HR);
+    int* ci_s = reinterpret_cast<int*>(hb + DH_CI);
+    const int bar_id = 1 + half;
+#define HSYNC() umma::bar_sync(bar_id, D_HALF)
+
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    const int n_tiles = a.bv.n_tiles;
+    const int off0 = sw_off(hw, l);
+    // timing experiments: GNODE_DBG bit 8 (256) = gathered rows without evict_last, bit 9 (512) = streams without evict_first
+    const uint64_t pol_keep = (a.dbg & 256) ? l2_policy_evict_normal() : l2_policy_evict_last();
+    const uint64_t pol_stream = (a.dbg & 512) ? l2_policy_evict_normal() : l2_policy_evict_first();
+
+    umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
+    if (tid < 32) umma::tmem_alloc(tslot, 256);
+    if (t == 0) {
+        umma::mbar_init(mbar, 1);
+        *seq_slot = a.counter ? atomicAdd(a.counter, 1) : 2 * (int)blockIdx.x + half;
+    }
+    umma::fence_before_sync();
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
+    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+    if (tid == 0) small[8] = a.p.s2_b[0];
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot + (uint32_t)half * 128u;             // this half's [128 x 80] fp32 accumulator
+    const uint32_t whi = umma::smem_u32(smem + D_WHI), wlo = umma::smem_u32(smem + D_WLO);
+    const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
+    const int q = warp & 3, cq = warp >> 2;                           // TMEM lane quarter / 16-column block of this warp
+    const int erow = q * 32 + lane;                                   // tile row this thread owns in the epilogues
+    uint32_t phase = 0;
+
+    int seq = *seq_slot;
+    auto prefetch_rows = [&](int2 sc) {            // thread 0 of the half; sc = schedule entry {tile, look-ahead row}
+        if (!(a.dbg & 32)) return;                 // off by default: on B200 the bulk L2 prefetches are evicted before use (+35 % DRAM reads)
+        const int t0 = sc.x * TILE;
+        const uint32_t bytes = (uint32_t)min(TILE, M - t0) * H * 4;
+        prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
+        prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
+        prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
+        prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
+        if (sc.y >= 0 && !(a.dbg & 1024)) prefetch_l2_bulk_hint(a.ip_in + (size_t)sc.y * H, (uint32_t)min(TILE, M - sc.y) * H * 4, pol_keep);
+    };
+    if (t == 0 && seq < n_tiles) prefetch_rows(a.bv.sched[seq]);
+
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define GN_TICK(i) if (a.tbuf && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
+    while (seq < n_tiles) {
+        int nseq = 0;
+        if (t == 0) nseq = a.counter ? atomicAdd(a.counter, 1) : seq + 2 * (int)gridDim.x;
+        const int tile = a.bv.tile_order[seq];
+        const int tile0 = tile * TILE;
+        const int nrows = min(TILE, M - tile0);
+        const int inst0 = a.bv.tile_inst[tile];
+        const int i_row0 = a.bv.inst[inst0].row0;
+        const bool single = (tile0 + nrows <= i_row0 + a.bv.inst[inst0].n);   // whole tile inside one instance
+        const int32_t* i_colidx = a.bv.inst[inst0].colidx;
+
+        // ---- P1: operand tiles for GEMM1 (S_k rows); rowptr slice, beta/gamma of the tile
+        {
+            const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+            float4 sreg[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                sreg[i] = (hw + 32 * i < nrows) ? ldg4(src + (size_t)i * 32 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 hi, lo;
+                umma::tf32_split4(sreg[i], hi, lo);
+                sts4(Xs, off0 + i * 4096, hi);
+                sts4(Ls, off0 + i * 4096, lo);
+            }
+        }
+        umma::fence_proxy_async();
+        if (t == 0) *row_ctr = 0;
+        if (single && t <= nrows) rp_s[t] = __ldg(a.bv.inst[inst0].rowptr + (tile0 - i_row0 + t));
+        if (t >= 256 && t < 256 + nrows) bg_s[t - 256] = a.beta[tile0 + t - 256];
+        if (t >= 384 && t < 384 + nrows) bg_s[TILE + t - 384] = a.gamma[tile0 + t - 384];
+        HSYNC();                                                                // S1
+        GN_TICK(0)
+        // ---- P2: GEMM1 || colidx staging ; S' epilogue (+ hid(S_k))
+        const bool do_g1 = !(a.dbg & 16), do_g2 = !(a.dbg & 8);       // timing experiments only
+        if (do_g1 && t == 0) umma::issue_split_gemm80(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        int ebase = 0;
+        if (single) {
+            ebase = rp_s[0];
+            const int ecnt = min(rp_s[nrows] - ebase, D_CAP);
+            for (int j = t; j < ecnt; j += D_HALF) ci_s[j] = i_colidx[ebase + j];   // instance-local ids: row0 is folded into lane_base
+        }
+        if (do_g1) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }        // hardware-suspended wait (no spinning)
+        umma::fence_after_sync();
+        if (do_g1) {
+            float v[16];
+            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+                float4 o;
+                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                sts4(Ls, sw_off(erow, 4 * cq + j), o);
+            }
+            if (cq == 0) {
+                float hv[4];
+                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                *reinterpret_cast<float4*>(hs_s + 4 * erow) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            }
+        }
+        umma::fence_before_sync();
+        HSYNC();                                                                // S2
+        GN_TICK(1)
+        int2 nsched = make_int2(0, -1);
+        if constexpr (FUSED) {
+        // ---- P3: per row (half-warp): own-row loads and the neighbour gather in flight together (one memory round
+        //      trip per row pair for degrees <= 8), SIR update, state stores, hid(R_k) -> smem, I_{k+1} hi/lo -> operand
+        //      tiles (S' is read from, and the lo part written to, the same 16 bytes by the same thread). Row pairs
+        //      are handed out dynamically so that hub rows do not leave the other warps idle.
+        {
+            const float* lane_base = a.ip_in + (size_t)i_row0 * H + 4 * l;
+            const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
+            float4 s, iv, rv, ipo;
+            auto load_own = [&](int rr) {
+                s = make_float4(1.f, 1.f, 1.f, 1.f); iv = s; rv = s; ipo = s;
+                if (rr < nrows && !(a.dbg & 4)) {
+                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
+                    s = ldg4_hint(a.y_in + off, pol_stream);
+                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
+                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
+                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
+                }
+            };
+            auto finish_row = [&](int rr, const float4 acc) {
+                const bool valid = rr < nrows;
+                float hv0 = 0.f, hv1 = 0.f, hv2 = 0.f, hv3 = 0.f;
+                if (valid) {
+                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
+                    const int so = sw_off(rr, l);
+                    const float4 sp = lds4(Ls, so);
+                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
+                    float4 sn, in_, rn;
+#define GN_COMP(c)                                                                  \
+    {                                                                               \
+        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
+        const float dR = __fmul_rn(ga, ipo.c);                                      \
+        const float dI = __fsub_rn(-dS, dR);                                        \
+        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
+        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
+        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
+    }
+                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+#undef GN_COMP
+                    stg4_hint(a.y_out + off, sn, pol_stream);
+                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
+                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
+                    float4 hi, lo;
+                    umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
+                    sts4(Xs, so, hi);
+                    sts4(Ls, so, lo);
+                    if (a.probs != nullptr) {                    // partial linear3 products of R_k (this lane's 4 channels)
+                        hv0 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l));
+                        hv1 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l));
+                        hv2 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l));
+                        hv3 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l));
+                    }
+                }
+                if (a.probs != nullptr) {
+                    // halving butterfly over the 16 lanes of the row: lanes 0 / 4 / 8 / 12 end with hid(R)[0 / 1 / 2 / 3]
+                    const float a0 = (b3 ? hv2 : hv0) + __shfl_xor_sync(0xffffffffu, b3 ? hv0 : hv2, 8);
+                    const float a1 = (b3 ? hv3 : hv1) + __shfl_xor_sync(0xffffffffu, b3 ? hv1 : hv3, 8);
+                    float c = (b2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b2 ? a0 : a1, 4);
+                    c += __shfl_xor_sync(0xffffffffu, c, 2);
+                    c += __shfl_xor_sync(0xffffffffu, c, 1);
+                    if (valid && (l & 3) == 0) hr_s[4 * rr + (l >> 2)] = c;
+                }
+            };
+            if (single) {
+                for (;;) {
+                    int p = 0;
+                    if (lane == 0) p = atomicAdd(row_ctr, 1);
+                    p = __shfl_sync(0xffffffffu, p, 0);
+                    if (p >= TILE / 2) break;
+                    const int rr = 2 * p + (lane >> 4);
+                    int e_rel = 0, deg = 0;
+                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
+                    load_own(rr);
+                    const int over = (e_rel + deg > D_CAP) ? 1 : 0;
+                    float4 acc;
+                    if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
+                        acc = gather_smem_nb<2>(lane_base, i_colidx + ebase + e_rel, deg, pol_keep);
+                    else
+                        acc = gather_smem_nb<2>(lane_base, ci_s + e_rel, deg, pol_keep);
+                    finish_row(rr, acc);
+                }
+            } else {                                         // tile spans several (small) instances
+                int inst = inst0;
+#pragma unroll 1
+                for (int it = 0; it < TILE / 32; ++it) {
+                    const int rr = hw + 32 * it;
+                    int row0 = 0, e0 = 0, deg = 0;
+                    const int32_t* ci = nullptr;
+                    if (rr < nrows) {
+                        const int g = tile0 + rr;
+                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                        const GnInstance I = a.bv.inst[inst];
+                        row0 = I.row0; ci = I.colidx;
+                        e0 = I.rowptr[g - row0];
+                        deg = I.rowptr[g - row0 + 1] - e0;
+                    }
+                    load_own(rr);
+                    const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                    finish_row(rr, acc);
+                }
+            }
+            if (t == 0) {
+                *seq_slot = nseq;
+                if (nseq < n_tiles) nsched = a.bv.sched[nseq];
+            }
+        }
+        GN_TICK(2)
+        } else {
+        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile; row pairs handed out dynamically
+        //      (the next pair's ticket is drawn before the current pair's loads, so its latency is hidden)
+        {
+            const float* lane_base = a.ip_in + (size_t)i_row0 * H + 4 * l;
+            const int zrow = M - i_row0;                     // the all-zero row that follows the I' rows
+            if (single) {
+                int p = 0;
+                if (lane == 0) p = atomicAdd(row_ctr, 1);
+                p = __shfl_sync(0xffffffffu, p, 0);
+                while (p < TILE / 2) {
+                    int pn = 0;
+                    if (lane == 0) pn = atomicAdd(row_ctr, 1);
+                    const int rr = 2 * p + (lane >> 4);
+                    int e_rel = 0, deg = 0;
+                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
+                    const int over = (e_rel + deg > D_CAP) ? 1 : 0;
+                    float4 acc;
+                    if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
+                        acc = gather_smem_z(lane_base, i_colidx + ebase + e_rel, deg, zrow, pol_keep);
+                    else
+                        acc = gather_smem_z(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
+                    sts4(Xs, sw_off(rr, l), acc);
+                    p = __shfl_sync(0xffffffffu, pn, 0);
+                }
+            } else {                                         // tile spans several (small) instances
+                int inst = inst0;
+#pragma unroll 1
+                for (int it = 0; it < TILE / 32; ++it) {
+                    const int rr = hw + 32 * it;
+                    int row0 = 0, e0 = 0, deg = 0;
+                    const int32_t* ci = nullptr;
+                    if (rr < nrows) {
+                        const int g = tile0 + rr;
+                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                        const GnInstance I = a.bv.inst[inst];
+                        row0 = I.row0; ci = I.colidx;
+                        e0 = I.rowptr[g - row0];
+                        deg = I.rowptr[g - row0 + 1] - e0;
+                    }
+                    const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                    sts4(Xs, off0 + it * 4096, acc);
+                }
+            }
+        }
+        HSYNC();                                                                // S2b: every AI row is parked
+        GN_TICK(2)
+        if (t == 0) {
+            *seq_slot = nseq;
+            if (nseq < n_tiles) nsched = a.bv.sched[nseq];
+        }
+        // ---- P3b: SIR update, stores; hid(R_k) -> smem; I_{k+1} hi/lo -> operand tiles. Two own-row register sets:
+        //      the loads of rows it and it+1 are in flight together (two exposed memory round trips per tile, not four).
+        {
+            struct Own { float4 s, iv, rv, ipo; };
+            auto load_own = [&](Own& o, int it) {
+                const int rr = hw + 32 * it;
+                o.s = make_float4(1.f, 1.f, 1.f, 1.f); o.iv = o.s; o.rv = o.s; o.ipo = o.s;
+                if (rr < nrows && !(a.dbg & 4)) {
+                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
+                    o.s = ldg4_hint(a.y_in + off, pol_stream);
+                    o.iv = ldg4_hint(a.y_in + plane + off, pol_stream);
+                    o.rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
+                    o.ipo = ldg4_hint(a.ip_in + off, pol_keep);
+                }
+            };
+            const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
+            auto process = [&](const Own& o, int it) {
+                const int rr = hw + 32 * it;
+                const bool valid = rr < nrows;
+                float hv0 = 0.f, hv1 = 0.f, hv2 = 0.f, hv3 = 0.f;
+                if (valid) {
+                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
+                    const float4 acc = lds4(Xs, off0 + it * 4096);
+                    const float4 sp = lds4(Ls, off0 + it * 4096);
+                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
+                    float4 sn, in_, rn;
+#define GN_COMP(c)                                                                  \
+    {                                                                               \
+        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
+        const float dR = __fmul_rn(ga, o.ipo.c);                                    \
+        const float dI = __fsub_rn(-dS, dR);                                        \
+        sn.c = __fadd_rn(o.s.c, __fmul_rn(dt, dS));                                 \
+        in_.c = __fadd_rn(o.iv.c, __fmul_rn(dt, dI));                               \
+        rn.c = __fadd_rn(o.rv.c, __fmul_rn(dt, dR));                                \
+    }
+                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+#undef GN_COMP
+                    stg4_hint(a.y_out + off, sn, pol_stream);
+                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
+                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
+                    float4 hi, lo;
+                    umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
+                    sts4(Xs, off0 + it * 4096, hi);
+                    sts4(Ls, off0 + it * 4096, lo);
+                    if (a.probs != nullptr) {                    // partial linear3 products of R_k (this lane's 4 channels)
+                        hv0 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l));
+                        hv1 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l));
+                        hv2 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l));
+                        hv3 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l));
+                    }
+                }
+                if (a.probs != nullptr) {
+                    // halving butterfly over the 16 lanes of the row: lanes 0 / 4 / 8 / 12 end with hid(R)[0 / 1 / 2 / 3]
+                    const float a0 = (b3 ? hv2 : hv0) + __shfl_xor_sync(0xffffffffu, b3 ? hv0 : hv2, 8);
+                    const float a1 = (b3 ? hv3 : hv1) + __shfl_xor_sync(0xffffffffu, b3 ? hv1 : hv3, 8);
+                    float c = (b2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b2 ? a0 : a1, 4);
+                    c += __shfl_xor_sync(0xffffffffu, c, 2);
+                    c += __shfl_xor_sync(0xffffffffu, c, 1);
+                    if (valid && (l & 3) == 0) hr_s[4 * rr + (l >> 2)] = c;
+                }
+            };
+            Own oa, ob;
+            load_own(oa, 0); load_own(ob, 1);
+            process(oa, 0);
+            process(ob, 1);
+            load_own(oa, 2); load_own(ob, 3);
+            process(oa, 2);
+            process(ob, 3);
+        }
+        }
+        GN_TICK(3)
+        umma::fence_proxy_async();
+        HSYNC();                                                                // S3
+        GN_TICK(4)
+        // ---- P4: GEMM2 || prefetch of the next tile || softmax of the input state ; I' epilogue (+ hid(I_{k+1}))
+        if (do_g2 && t == 0) umma::issue_split_gemm80(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        const int seq_next = *seq_slot;
+        if (t == 0 && seq_next < n_tiles) prefetch_rows(nsched);
+        if (a.probs != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
+            const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
+            const float4 hR = *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            const float4 hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
+            const float4 b3v = *reinterpret_cast<const float4*>(small);
+            const float4 w2v = *reinterpret_cast<const float4*>(small + 4);
+            const float b2v = small[8];
+#define GN_DEC(h) fmaf(w2v.w, fmaxf(h.w + b3v.w, 0.f), fmaf(w2v.z, fmaxf(h.z + b3v.z, 0.f), fmaf(w2v.y, fmaxf(h.y + b3v.y, 0.f), fmaf(w2v.x, fmaxf(h.x + b3v.x, 0.f), b2v))))
+            const float oS = GN_DEC(hS), oI = GN_DEC(hI), oR = GN_DEC(hR);
+#undef GN_DEC
+            const float mx = fmaxf(oS, fmaxf(oI, oR));
+            const float eS = ex2_approx((oS - mx) * 1.4426950408889634f), eI = ex2_approx((oI - mx) * 1.4426950408889634f),
+                        eR = ex2_approx((oR - mx) * 1.4426950408889634f);
+            const float inv = rcp_approx(eS + eI + eR);
+            float* pr = a.probs + (size_t)(tile0 + t) * 3;
+            pr[0] = eS * inv; pr[1] = eI * inv; pr[2] = eR * inv;
+        }
+        if (do_g2) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }
+        umma::fence_after_sync();
+        if (do_g2) {
+            float v[16];
+            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+                float4 o;
+                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                sts4(Ls, sw_off(erow, 4 * cq + j), o);
+            }
+            if (cq == 0) {
+                float hv[4];
+                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                if (erow < nrows) *reinterpret_cast<float4*>(a.hid_i + (size_t)(tile0 + erow) * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            }
+        }
+        umma::fence_before_sync();
+        HSYNC();                                                                // S4
+        GN_TICK(5)
+        // ---- P5: coalesced store of I'_{k+1}
+        {
+            float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (hw + 32 * i < nrows) stg4_hint(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096), pol_stream);
+        }
+        HSYNC();                                                                // S5
+        GN_TICK(6)
+        seq = seq_next;
+    }
+    if (a.tbuf && tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
+#undef GN_TICK
+#undef HSYNC
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(*tslot, 256);
+}
+
+// Decoder + softmax of one stored state (the last grid point of the dual-kernel rollout): probs = softmax over
+// {S, I, R} of linearS2(relu(linear3(.)))  (ode_nn_ngraph_sim.py:170-188). Half-warp per row.
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ y, float* __restrict__ probs, int M, const gnode_params_t p) {
+    __shared__ __align__(16) float W3s[4 * H];
+    __shared__ float small[16];
+    const int tid = threadIdx.x, l = tid & 15;
+    for (int i = tid; i < 4 * H; i += 256) W3s[i] = p.l3_w[i];
+    if (tid < 4) { small[tid] = p.l3_b[tid]; small[4 + tid] = p.s2_w[tid]; }
+    if (tid == 0) small[8] = p.s2_b[0];
+    __syncthreads();
+    const size_t plane = (size_t)M * H;
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + (tid >> 5)) * 2; base < M; base += (int64_t)gridDim.x * 16) {
+        const int64_t g = base + ((tid >> 4) & 1);
+        const bool valid = g < M;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), i = s, r = s;
+        if (valid) {
+            const size_t off = (size_t)g * H + 4 * l;
+            s = ldg4_stream(y + off); i = ldg4_stream(y + plane + off); r = ldg4_stream(y + 2 * plane + off);
+        }
+        decode_row(s, i, r, W3s, small, l, valid, probs + (size_t)(valid ? g : 0) * 3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp-specialised fused Euler step (1 CTA of 640 threads per SM, two tile slots in flight).
 //
 //   PE-A group (4 warps = the four TMEM lane quarters): for tile t in slot t&1 (after slot_free)
@@ -1039,15 +1601,38 @@ static int launch_step_ws(const gnode_batch* b, const StepArgs& a, cudaStream_t 
     return GNODE_OK;
 }
 
-static int step_kernel_choice() {     // 1 = phase-structured (default), 2 = warp-specialised, 0 = generic
-    static int c = -1;
-    if (c < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); c = e ? atoi(e) : 1; }
-    return c;
+template <bool FAST, bool FUSED>
+static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const int grid = std::min((b->n_tiles + 1) / 2, b->sm_count);
+    step_dual_kernel<FAST, FUSED><<<grid, D_THREADS, D_TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
 }
+
+// 3 = dual (default: two tile pipelines per CTA, decoder hidden layer on the tensor core), 1 = phase-structured,
+// 2 = warp-specialised, 0 = generic
+static int g_step_kernel = -1;
+static int step_kernel_choice() {
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? (atoi(e) & 3) : 3; }
+    return g_step_kernel;
+}
+
+// the dual kernel emits probs[k] of its INPUT state and needs the hid_i side buffer (tensor-core variants only)
+static bool use_dual() { return (current_variant() & VAR_TC) && step_kernel_choice() == 3; }
 
 template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
+    if (MODE == MODE_STEP && use_dual()) {
+        static const bool fused = getenv("GNODE_FUSED_ROWS") && atoi(getenv("GNODE_FUSED_ROWS")) != 0;   // experiment switch
+        if (fused) return (var & VAR_FASTSIG) ? launch_step_dual<true, true>(b, a, stream) : launch_step_dual<false, true>(b, a, stream);
+        return (var & VAR_FASTSIG) ? launch_step_dual<true, false>(b, a, stream) : launch_step_dual<false, false>(b, a, stream);
+    }
     if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 2)
         return (var & VAR_FASTSIG) ? launch_step_ws<true>(b, a, stream) : launch_step_ws<false>(b, a, stream);
     if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 1)
@@ -1072,6 +1657,12 @@ extern "C" int gnode_set_variant(int variant) {
     return GNODE_OK;
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
+extern "C" int gnode_set_step_kernel(int kernel) {
+    if (kernel < 0 || kernel > 3) { set_error("gnode_set_step_kernel: kernel must be 0..3"); return GNODE_ERR_ARG; }
+    g_step_kernel = kernel;
+    return GNODE_OK;
+}
+extern "C" int gnode_get_step_kernel(void) { return step_kernel_choice(); }
 extern "C" int gnode_debug_phase_cycles(long long* out8) {
     if (!out8) return GNODE_ERR_ARG;
     for (int i = 0; i < 8; ++i) out8[i] = 0;
@@ -1088,7 +1679,8 @@ extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) 
     const size_t M = (size_t)b->M;
     size_t bytes = 2 * align_up(M * sizeof(float), 256);          // beta, gamma
     bytes += 4096;                                                // tile-scheduler counters (one int per launch)
-    bytes += 2 * align_up(M * H * sizeof(float), 256);            // I' ping-pong
+    bytes += 2 * align_up((M + 1) * H * sizeof(float), 256);      // I' ping-pong (+ one all-zero row each)
+    bytes += align_up(M * 4 * sizeof(float), 256);                // hid_i: linear3 pre-activations of the I block
     if (!with_traj) bytes += 2 * align_up(3 * M * H * sizeof(float), 256);  // state ping-pong
     return bytes;
 }
@@ -1113,8 +1705,11 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     int* counters = (int*)ws;  ws += 4096;
     GN_CUDA(cudaMemsetAsync(counters, 0, 4096, stream));
     float* ip[2];
-    ip[0] = (float*)ws; ws += align_up(M * H * sizeof(float), 256);
-    ip[1] = (float*)ws; ws += align_up(M * H * sizeof(float), 256);
+    ip[0] = (float*)ws; ws += align_up((M + 1) * H * sizeof(float), 256);
+    ip[1] = (float*)ws; ws += align_up((M + 1) * H * sizeof(float), 256);
+    GN_CUDA(cudaMemsetAsync(ip[0] + M * H, 0, H * sizeof(float), stream));      // row M: the zero row padded gather slots read
+    GN_CUDA(cudaMemsetAsync(ip[1] + M * H, 0, H * sizeof(float), stream));
+    float* hid_i = (float*)ws; ws += align_up(M * 4 * sizeof(float), 256);
     float* st[2] = {nullptr, nullptr};
     if (!traj) {
         st[0] = (float*)ws; ws += align_up(3 * M * H * sizeof(float), 256);
@@ -1137,16 +1732,24 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
         a.tbuf = g_tbuf;
     }
     a.counter = (a.dbg & 64) ? nullptr : counters;
-    int rc = launch_step<MODE_ENCODE>(b, a, stream);
+    const bool dual = use_dual();
+    a.hid_i = dual ? hid_i : nullptr;
+    int rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
     for (int k = 0; k + 1 < T; ++k) {
         a.y_in = state(k); a.y_out = state(k + 1);
         a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
-        a.probs = probs + (size_t)(k + 1) * M * 3;
+        // dual kernel: step k decodes its input state k (k = 0 is the encoder's); the others decode their output
+        a.probs = dual ? (k > 0 ? probs + (size_t)k * M * 3 : nullptr) : probs + (size_t)(k + 1) * M * 3;
         a.dt = dt_host[k];
         a.counter = (k + 1 < 1024 && !(a.dbg & 64)) ? counters + (k + 1) : nullptr;
         rc = launch_step<MODE_STEP>(b, a, stream);
         if (rc) return rc;
+    }
+    if (dual && T > 1) {                                   // the last grid state
+        const int grid = (int)std::min<int64_t>(((int64_t)M + 15) / 16, (int64_t)b->sm_count * 16);
+        decode_kernel<<<grid, 256, 0, stream>>>(state(T - 1), probs + (size_t)(T - 1) * M * 3, (int)M, *p);
+        GN_LAUNCH_CHECK();
     }
     return GNODE_OK;
 }
@@ -1162,7 +1765,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;

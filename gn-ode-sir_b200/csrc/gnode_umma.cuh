@@ -46,6 +46,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// same, with a suspend-time hint: the hardware parks the thread until the phase completes or ~20 us pass,
+// so waiting warps consume (almost) no issue slots
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (!done && ++spins > (1u << 16)) __trap();      // > 1 s: a lost completion must fault, never hang the GPU
+    } while (!done);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -86,6 +99,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 4 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ---- TF32 split: x = hi + lo + O(2^-23 |x|), hi = rna_tf32(x), lo = rna_tf32(x - hi); both have their
@@ -140,6 +163,48 @@ __device__ __forceinline__ void issue_split_gemm_to(uint32_t tmem, uint64_t* bar
         for (int k = 0; k < 8; ++k) {
             const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
             const uint32_t boff = ((k >> 2) << 13) + ((k & 3) << 5);
+            mma_tf32(tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
+            acc = 1;
+        }
+    }
+    mma_commit(bar);
+}
+
+// ---- N = 80 variant: the B operand stacks linear.weight (rows 0..63) on linear3.weight (rows 64..67, rows 68..79
+// zero), so the accumulator columns 64..67 hold the decoder's hidden pre-activations of the same rows
+// (ode_nn_ngraph_sim.py:172-176) at no extra operand traffic. K-block stride of the 80-row operand: 80 * 128 B.
+constexpr int NB80 = 80;
+constexpr int WB80_KBLOCK = NB80 * 128;            // 10240 B (1024-B aligned)
+constexpr int WB80_BYTES = 2 * WB80_KBLOCK;        // 20480 B per operand (hi or lo)
+__device__ __forceinline__ int swb80_off(int n, int c4) { return (c4 >> 3) * WB80_KBLOCK + (n << 7) + (((c4 & 7) ^ (n & 7)) << 4); }
+
+__device__ __forceinline__ void prepare_weights80(const float* __restrict__ W, const float* __restrict__ W3, unsigned char* Whi,
+                                                  unsigned char* Wlo, int tid, int nthreads) {
+    for (int idx = tid; idx < NB80 * CHUNKS; idx += nthreads) {
+        const int n = idx >> 4, c4 = idx & 15;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+        if (n < H) x = ldg4(W + n * H + 4 * c4);
+        else if (n < H + 4) x = ldg4(W3 + (n - H) * H + 4 * c4);
+        tf32_split4(x, hi, lo);
+        sts4(Whi, swb80_off(n, c4), hi);
+        sts4(Wlo, swb80_off(n, c4), lo);
+    }
+    fence_proxy_async();
+}
+
+// One thread: D[128 x 80] (TMEM columns tmem .. tmem+79) = X [W; W3]^T as the 4-term split product, then commit.
+__device__ __forceinline__ void issue_split_gemm80(uint32_t tmem, uint64_t* bar, uint32_t whi, uint32_t wlo, uint32_t xhi, uint32_t xlo) {
+    fence_after_sync();
+    constexpr uint32_t idesc = instr_desc_tf32(TILE, NB80);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const uint32_t abase = (pass < 2) ? xlo : xhi;
+        const uint32_t bbase = (pass == 0 || pass == 2) ? wlo : whi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
+            const uint32_t boff = (uint32_t)(k >> 2) * WB80_KBLOCK + ((k & 3) << 5);
             mma_tf32(tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
             acc = 1;
         }

@@ -69,3 +69,48 @@ def test_variant_large_graph_fp64(gn, variant):
     err_ref = (g.probs32.double() - ref64).abs().max().item()
     print("variant %d fb-social: err vs fp64 ours %.3e, reference fp32 %.3e" % (variant, err_ours, err_ref))
     assert err_ours <= max(1e-5, 2.0 * err_ref), (err_ours, err_ref)
+
+
+STEP_KERNELS = {3: "dual", 1: "phase", 2: "warp-specialised", 0: "generic"}
+
+
+@pytest.fixture
+def step_kernel(gn, request):
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
+    prev = L.gnode_get_step_kernel()
+    _lib.check(L.gnode_set_step_kernel(request.param), "gnode_set_step_kernel")
+    yield request.param
+    L.gnode_set_step_kernel(prev)
+
+
+@pytest.mark.parametrize("step_kernel", list(STEP_KERNELS), indirect=True, ids=list(STEP_KERNELS.values()))
+@pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if "fbsocial" not in c])
+def test_step_kernel_rollout_matches_reference(gn, step_kernel, name):
+    """Every structure of the tensor-core step kernel against the reference's own outputs (bar 1e-5)."""
+    g = Golden(name)
+    probs = run_cuda(gn, g)
+    err = (probs[:: g.tstride] - g.probs32).abs().max().item()
+    print("step kernel %d %s: max|cuda - reference| = %.3e" % (step_kernel, name, err))
+    assert err < 1e-5, err
+
+
+def test_step_kernels_agree_on_training_trajectory(gn):
+    """Forward with a stored trajectory (training): the dual kernel's probabilities of EVERY grid point, including
+    the first (encoder) and the last (decode kernel), agree with the phase-structured kernel's."""
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
+    g = Golden("sim_fbfood_b2")
+    prev = L.gnode_get_step_kernel()
+    out = {}
+    try:
+        for k in (3, 1):
+            _lib.check(L.gnode_set_step_kernel(k), "gnode_set_step_kernel")
+            ps = [p.requires_grad_() for p in dev_params(g.params)]
+            dt = gn.rollout.dt_array(orc.time_grid(g.maxTime, g.deltaT))
+            out[k] = gn.rollout.rollout(g.x.to(DEV), make_batch(gn, g), dt, ps).detach().cpu()
+    finally:
+        L.gnode_set_step_kernel(prev)
+    err = (out[3] - out[1]).abs().max().item()
+    print("dual vs phase (training forward): %.3e" % err)
+    assert err < 2e-6, err

@@ -23,6 +23,11 @@ names_ws = ["WK wait csr", "WK rows (gather+update)", "WK wait S'", "PEA wait fr
 names = ["P1 load+split..S1", "P2 mma1+ci+E1..S2", "P3a gather", "P3b update+decode", "S3 wait", "P4 mma2+E2..S4", "P5 store..S5", "-"]
 tiles = 39 * ((trials * N + 127) // 128)
 print("tiles", tiles, "total cycles/tile %.0f" % (v.sum() / tiles))
-if os.environ.get("GNODE_STEP_KERNEL", "2") == "2": names = names_ws
+names_dual = ["P1 load+split..S1", "P2 mma1+ci+E1..S2", "P3 gather+update", "-", "S3 wait", "P4 mma2+softmax+E2..S4", "P5 store..S5", "-"]
+kern = os.environ.get("GNODE_STEP_KERNEL", "3")
+if kern == "2": names = names_ws
+if kern == "3":
+    names = names_dual
+    tiles = tiles / 2      # only half 0 of every CTA is instrumented
 for n, c in zip(names, v):
     print("%-22s %8.0f cycles/tile  %5.1f%%" % (n, c / tiles, 100 * c / v.sum()))
