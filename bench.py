@@ -265,7 +265,7 @@ def main():
     traffic = ncu_traffic_per_launch(rows)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "kernel": "gnode::step_tc_kernel (fused Euler step, tcgen05)", "launch_ms": step_ms, "rows_per_launch": rows,
+                "kernel": "gnode::step_dual_kernel (fused Euler step, tcgen05; encoder + final decode launches charged to it)", "launch_ms": step_ms, "rows_per_launch": rows,
                 "algorithmic_bytes_per_node_step": ALGO_BYTES_PER_NODE_STEP, "peak_source": peak_src}
     del S, I, R
 

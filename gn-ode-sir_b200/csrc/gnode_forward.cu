@@ -664,10 +664,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
 // so the launch of step k emits probs[k] (the softmax of its INPUT state, one thread per row) instead of probs[k+1];
 // the host decodes the last state with decode_kernel. Differences from step_tc_kernel besides that:
 //   * the tcgen05.commit mbarrier is awaited with a suspend-time hint (the hardware parks the warps; no spin loop);
-//   * the gather and the update are one row phase: a row's own-row loads and its neighbour loads are in flight
-//     together, and the gather is specialised by ceil(deg / 4) (no 11-wide predicated tail).
+//   * no tile starts with a chain of dependent loads: an idle warp resolves the next tile's metadata during the
+//     second GEMM, the next tile's S rows are prefetched into registers during the I' store, and the CSR slice,
+//     beta/gamma and S rows of a tile are all in flight together;
+//   * the gather is specialised by the exact degree (1..12 rows per round trip) and reads an all-zero row for the
+//     padding slots instead of predicating; no L2 bulk prefetch (measured: evicted before use on B200).
 constexpr int D_THREADS = 1024, D_HALF = 512;
-constexpr int D_CAP = 1536;                               // colidx entries staged per tile (total smem <= 192 KB keeps >= 64 KB of L1)
+constexpr int D_CAP = 1536;                               // colidx entries staged per tile = 3 per thread (total smem <= 196 KB keeps 60 KB of L1)
 constexpr int D_WHI = 0;
 constexpr int D_WLO = umma::WB80_BYTES;
 constexpr int D_B = 2 * umma::WB80_BYTES;                 // bias [64]
@@ -678,8 +681,9 @@ constexpr int D_SHARED = 43008;                           // shared part, rounde
 static_assert(D_TSLOT + 16 <= D_SHARED, "shared part overflows");
 constexpr int DH_X = 0;                                   // 32 KB  A operand hi / parked neighbour sums
 constexpr int DH_L = 32768;                               // 32 KB  A operand lo / S' / I' staging
-constexpr int DH_MBAR = 65536;                            // mbarrier (8) + sequence slot (4) + row-pair counter (4)
-constexpr int DH_BG = DH_MBAR + 32;                       // beta[TILE], gamma[TILE]
+constexpr int DH_MBAR = 65536;                            // mbarrier (8) + row-pair counter (4)
+constexpr int DH_META = DH_MBAR + 16;                     // DTileMeta of the coming tile (48 B)
+constexpr int DH_BG = DH_META + 48;                       // beta[TILE], gamma[TILE]
 constexpr int DH_RP = DH_BG + 2 * TILE * 4;               // rowptr slice [TILE + 1] (+pad)
 constexpr int DH_HS = DH_RP + 544;                        // hid(S_k) [TILE][4]
 constexpr int DH_HR = DH_HS + TILE * 16;                  // hid(R_k) [TILE][4]
@@ -755,7 +759,21 @@ __device__ __forceinline__ float4 gather_smem_z(const float* __restrict__ lane_b
     return acc;
 }
 
-template <bool FAST, bool FUSED>
+// Tile metadata of one pipeline (shared memory): everything the next tile needs, fetched by an otherwise idle warp
+// while the current tile's second GEMM runs, so no tile starts with a chain of dependent global loads.
+struct DTileMeta {
+    const int32_t* rowptr;   // of the owning instance, already offset to the tile's first row
+    const int32_t* colidx;   // of the owning instance
+    int seq;                 // sequence number (>= n_tiles: no more tiles)
+    int tile0;               // first global row
+    int nrows;
+    int i_row0;              // first global row of the owning instance
+    int single;              // whole tile inside one instance
+    int ebase, ecnt;         // CSR entry range of the tile (single tiles)
+    int inst0;
+};
+
+template <bool FAST>
 __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -772,8 +790,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
     float* small = reinterpret_cast<float*>(smem + D_SMALL);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + D_TSLOT);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(hb + DH_MBAR);
-    int* seq_slot = reinterpret_cast<int*>(hb + DH_MBAR + 8);
-    int* row_ctr = reinterpret_cast<int*>(hb + DH_MBAR + 12);
+    int* row_ctr = reinterpret_cast<int*>(hb + DH_MBAR + 8);
+    DTileMeta* meta = reinterpret_cast<DTileMeta*>(hb + DH_META);
     float* bg_s = reinterpret_cast<float*>(hb + DH_BG);
     int* rp_s = reinterpret_cast<int*>(hb + DH_RP);
     float* hs_s = reinterpret_cast<float*>(hb + DH_HS);
@@ -790,12 +808,29 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
     const uint64_t pol_keep = (a.dbg & 256) ? l2_policy_evict_normal() : l2_policy_evict_last();
     const uint64_t pol_stream = (a.dbg & 512) ? l2_policy_evict_normal() : l2_policy_evict_first();
 
+    // one thread: draw the next sequence number and resolve its metadata (3 dependent loads of small tables)
+    auto fetch_meta = [&](int k) {
+        int seq = a.counter ? atomicAdd(a.counter, 1) : 2 * (int)blockIdx.x + half + 2 * k * (int)gridDim.x;
+        if ((a.dbg & 2048) && half == 1) seq = n_tiles;               // timing experiment: one pipeline per SM
+        DTileMeta m;
+        m.seq = seq; m.rowptr = nullptr; m.colidx = nullptr;
+        m.tile0 = 0; m.nrows = 0; m.i_row0 = 0; m.single = 0; m.ebase = 0; m.ecnt = 0; m.inst0 = 0;
+        if (seq < n_tiles) {
+            const int tile = a.bv.tile_order[seq];
+            const int4 tm = a.bv.tile_meta[tile];                     // {ebase, ecnt, inst0, single}
+            const GnInstance I = a.bv.inst[tm.z];
+            m.tile0 = tile * TILE;
+            m.nrows = min(TILE, M - m.tile0);
+            m.i_row0 = I.row0; m.single = tm.w; m.ebase = tm.x; m.ecnt = tm.y; m.inst0 = tm.z;
+            m.rowptr = I.rowptr + (m.tile0 - I.row0);
+            m.colidx = I.colidx;
+        }
+        *meta = m;
+    };
+
     umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
     if (tid < 32) umma::tmem_alloc(tslot, 256);
-    if (t == 0) {
-        umma::mbar_init(mbar, 1);
-        *seq_slot = a.counter ? atomicAdd(a.counter, 1) : 2 * (int)blockIdx.x + half;
-    }
+    if (t == 0) { umma::mbar_init(mbar, 1); fetch_meta(0); }
     umma::fence_before_sync();
     if (tid < H) bs[tid] = a.p.lin_b[tid];
     if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
@@ -809,41 +844,39 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
     const int q = warp & 3, cq = warp >> 2;                           // TMEM lane quarter / 16-column block of this warp
     const int erow = q * 32 + lane;                                   // tile row this thread owns in the epilogues
     uint32_t phase = 0;
+    int kfetch = 1;
 
-    int seq = *seq_slot;
-    auto prefetch_rows = [&](int2 sc) {            // thread 0 of the half; sc = schedule entry {tile, look-ahead row}
-        if (!(a.dbg & 32)) return;                 // off by default: on B200 the bulk L2 prefetches are evicted before use (+35 % DRAM reads)
-        const int t0 = sc.x * TILE;
-        const uint32_t bytes = (uint32_t)min(TILE, M - t0) * H * 4;
-        prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
-        prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
-        prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
-        prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
-        if (sc.y >= 0 && !(a.dbg & 1024)) prefetch_l2_bulk_hint(a.ip_in + (size_t)sc.y * H, (uint32_t)min(TILE, M - sc.y) * H * 4, pol_keep);
+    // S_k rows of the tile (4 rows x 16 B per thread)
+    float4 sreg[4];
+    auto load_s = [&](int tile0, int nrows) {
+        const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            sreg[i] = (hw + 32 * i < nrows) ? ldg4_hint(src + (size_t)i * 32 * H, pol_stream) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (t == 0 && seq < n_tiles) prefetch_rows(a.bv.sched[seq]);
-
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
 #define GN_TICK(i) if (a.tbuf && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
-    while (seq < n_tiles) {
-        int nseq = 0;
-        if (t == 0) nseq = a.counter ? atomicAdd(a.counter, 1) : seq + 2 * (int)gridDim.x;
-        const int tile = a.bv.tile_order[seq];
-        const int tile0 = tile * TILE;
-        const int nrows = min(TILE, M - tile0);
-        const int inst0 = a.bv.tile_inst[tile];
-        const int i_row0 = a.bv.inst[inst0].row0;
-        const bool single = (tile0 + nrows <= i_row0 + a.bv.inst[inst0].n);   // whole tile inside one instance
-        const int32_t* i_colidx = a.bv.inst[inst0].colidx;
+    for (;;) {
+        const DTileMeta m = *meta;                                    // written before the last barrier passed
+        if (m.seq >= n_tiles) break;
+        const int tile0 = m.tile0, nrows = m.nrows, i_row0 = m.i_row0, ebase = m.ebase;
+        const bool single = m.single != 0;
 
-        // ---- P1: operand tiles for GEMM1 (S_k rows); rowptr slice, beta/gamma of the tile
+        // ---- P1: operand tiles for GEMM1 (S_k rows); the tile's CSR slice, beta/gamma -> smem
+        //      (every address is known from the metadata: all these loads are in flight together)
         {
-            const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
-            float4 sreg[4];
+            load_s(tile0, nrows);
+            int rpv = 0, civ[3] = {0, 0, 0};
+            float bgv = 0.f;
+            const int ecnt = min(m.ecnt, D_CAP);
+            if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
+            if (single) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                sreg[i] = (hw + 32 * i < nrows) ? ldg4(src + (size_t)i * 32 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 3; ++u) if (t + u * D_HALF < ecnt) civ[u] = __ldg(m.colidx + ebase + t + u * D_HALF);
+            }
+            if (t >= 256 && t < 256 + nrows) bgv = a.beta[tile0 + t - 256];
+            if (t >= 384 && t < 384 + nrows) bgv = a.gamma[tile0 + t - 384];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float4 hi, lo;
@@ -851,23 +884,21 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                 sts4(Xs, off0 + i * 4096, hi);
                 sts4(Ls, off0 + i * 4096, lo);
             }
+            umma::fence_proxy_async();
+            if (t == 0) *row_ctr = 0;
+            if (single && t <= nrows) rp_s[t] = rpv;
+            if (single) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) if (t + u * D_HALF < ecnt) ci_s[t + u * D_HALF] = civ[u];   // instance-local ids
+            }
+            if (t >= 256 && t < 256 + nrows) bg_s[t - 256] = bgv;
+            if (t >= 384 && t < 384 + nrows) bg_s[TILE + t - 384] = bgv;
         }
-        umma::fence_proxy_async();
-        if (t == 0) *row_ctr = 0;
-        if (single && t <= nrows) rp_s[t] = __ldg(a.bv.inst[inst0].rowptr + (tile0 - i_row0 + t));
-        if (t >= 256 && t < 256 + nrows) bg_s[t - 256] = a.beta[tile0 + t - 256];
-        if (t >= 384 && t < 384 + nrows) bg_s[TILE + t - 384] = a.gamma[tile0 + t - 384];
         HSYNC();                                                                // S1
         GN_TICK(0)
-        // ---- P2: GEMM1 || colidx staging ; S' epilogue (+ hid(S_k))
+        // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         const bool do_g1 = !(a.dbg & 16), do_g2 = !(a.dbg & 8);       // timing experiments only
         if (do_g1 && t == 0) umma::issue_split_gemm80(tmem, mbar, whi, wlo, xs_addr, ls_addr);
-        int ebase = 0;
-        if (single) {
-            ebase = rp_s[0];
-            const int ecnt = min(rp_s[nrows] - ebase, D_CAP);
-            for (int j = t; j < ecnt; j += D_HALF) ci_s[j] = i_colidx[ebase + j];   // instance-local ids: row0 is folded into lane_base
-        }
         if (do_g1) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }        // hardware-suspended wait (no spinning)
         umma::fence_after_sync();
         if (do_g1) {
@@ -890,115 +921,6 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         umma::fence_before_sync();
         HSYNC();                                                                // S2
         GN_TICK(1)
-        int2 nsched = make_int2(0, -1);
-        if constexpr (FUSED) {
-        // ---- P3: per row (half-warp): own-row loads and the neighbour gather in flight together (one memory round
-        //      trip per row pair for degrees <= 8), SIR update, state stores, hid(R_k) -> smem, I_{k+1} hi/lo -> operand
-        //      tiles (S' is read from, and the lo part written to, the same 16 bytes by the same thread). Row pairs
-        //      are handed out dynamically so that hub rows do not leave the other warps idle.
-        {
-            const float* lane_base = a.ip_in + (size_t)i_row0 * H + 4 * l;
-            const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
-            float4 s, iv, rv, ipo;
-            auto load_own = [&](int rr) {
-                s = make_float4(1.f, 1.f, 1.f, 1.f); iv = s; rv = s; ipo = s;
-                if (rr < nrows && !(a.dbg & 4)) {
-                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                    s = ldg4_hint(a.y_in + off, pol_stream);
-                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
-                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
-                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
-                }
-            };
-            auto finish_row = [&](int rr, const float4 acc) {
-                const bool valid = rr < nrows;
-                float hv0 = 0.f, hv1 = 0.f, hv2 = 0.f, hv3 = 0.f;
-                if (valid) {
-                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                    const int so = sw_off(rr, l);
-                    const float4 sp = lds4(Ls, so);
-                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
-                    float4 sn, in_, rn;
-#define GN_COMP(c)                                                                  \
-    {                                                                               \
-        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
-        const float dR = __fmul_rn(ga, ipo.c);                                      \
-        const float dI = __fsub_rn(-dS, dR);                                        \
-        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
-        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
-        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
-    }
-                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
-#undef GN_COMP
-                    stg4_hint(a.y_out + off, sn, pol_stream);
-                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
-                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
-                    float4 hi, lo;
-                    umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
-                    sts4(Xs, so, hi);
-                    sts4(Ls, so, lo);
-                    if (a.probs != nullptr) {                    // partial linear3 products of R_k (this lane's 4 channels)
-                        hv0 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l));
-                        hv1 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l));
-                        hv2 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l));
-                        hv3 = dot4(rv, *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l));
-                    }
-                }
-                if (a.probs != nullptr) {
-                    // halving butterfly over the 16 lanes of the row: lanes 0 / 4 / 8 / 12 end with hid(R)[0 / 1 / 2 / 3]
-                    const float a0 = (b3 ? hv2 : hv0) + __shfl_xor_sync(0xffffffffu, b3 ? hv0 : hv2, 8);
-                    const float a1 = (b3 ? hv3 : hv1) + __shfl_xor_sync(0xffffffffu, b3 ? hv1 : hv3, 8);
-                    float c = (b2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b2 ? a0 : a1, 4);
-                    c += __shfl_xor_sync(0xffffffffu, c, 2);
-                    c += __shfl_xor_sync(0xffffffffu, c, 1);
-                    if (valid && (l & 3) == 0) hr_s[4 * rr + (l >> 2)] = c;
-                }
-            };
-            if (single) {
-                for (;;) {
-                    int p = 0;
-                    if (lane == 0) p = atomicAdd(row_ctr, 1);
-                    p = __shfl_sync(0xffffffffu, p, 0);
-                    if (p >= TILE / 2) break;
-                    const int rr = 2 * p + (lane >> 4);
-                    int e_rel = 0, deg = 0;
-                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
-                    load_own(rr);
-                    const int over = (e_rel + deg > D_CAP) ? 1 : 0;
-                    float4 acc;
-                    if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
-                        acc = gather_smem_nb<2>(lane_base, i_colidx + ebase + e_rel, deg, pol_keep);
-                    else
-                        acc = gather_smem_nb<2>(lane_base, ci_s + e_rel, deg, pol_keep);
-                    finish_row(rr, acc);
-                }
-            } else {                                         // tile spans several (small) instances
-                int inst = inst0;
-#pragma unroll 1
-                for (int it = 0; it < TILE / 32; ++it) {
-                    const int rr = hw + 32 * it;
-                    int row0 = 0, e0 = 0, deg = 0;
-                    const int32_t* ci = nullptr;
-                    if (rr < nrows) {
-                        const int g = tile0 + rr;
-                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
-                        const GnInstance I = a.bv.inst[inst];
-                        row0 = I.row0; ci = I.colidx;
-                        e0 = I.rowptr[g - row0];
-                        deg = I.rowptr[g - row0 + 1] - e0;
-                    }
-                    load_own(rr);
-                    const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
-                    finish_row(rr, acc);
-                }
-            }
-            if (t == 0) {
-                *seq_slot = nseq;
-                if (nseq < n_tiles) nsched = a.bv.sched[nseq];
-            }
-        }
-        GN_TICK(2)
-        } else {
         // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile; row pairs handed out dynamically
         //      (the next pair's ticket is drawn before the current pair's loads, so its latency is hidden)
         {
@@ -1017,14 +939,14 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                     const int over = (e_rel + deg > D_CAP) ? 1 : 0;
                     float4 acc;
                     if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
-                        acc = gather_smem_z(lane_base, i_colidx + ebase + e_rel, deg, zrow, pol_keep);
+                        acc = gather_smem_z(lane_base, m.colidx + ebase + e_rel, deg, zrow, pol_keep);
                     else
                         acc = gather_smem_z(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
                     sts4(Xs, sw_off(rr, l), acc);
                     p = __shfl_sync(0xffffffffu, pn, 0);
                 }
             } else {                                         // tile spans several (small) instances
-                int inst = inst0;
+                int inst = m.inst0;
 #pragma unroll 1
                 for (int it = 0; it < TILE / 32; ++it) {
                     const int rr = hw + 32 * it;
@@ -1045,10 +967,6 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         }
         HSYNC();                                                                // S2b: every AI row is parked
         GN_TICK(2)
-        if (t == 0) {
-            *seq_slot = nseq;
-            if (nseq < n_tiles) nsched = a.bv.sched[nseq];
-        }
         // ---- P3b: SIR update, stores; hid(R_k) -> smem; I_{k+1} hi/lo -> operand tiles. Two own-row register sets:
         //      the loads of rows it and it+1 are in flight together (two exposed memory round trips per tile, not four).
         {
@@ -1086,21 +1004,23 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
     }
                     GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
 #undef GN_COMP
+                    if (!(a.dbg & 4096)) {
                     stg4_hint(a.y_out + off, sn, pol_stream);
                     stg4_hint(a.y_out + plane + off, in_, pol_stream);
                     stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
+                    }
                     float4 hi, lo;
                     umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
                     sts4(Xs, off0 + it * 4096, hi);
                     sts4(Ls, off0 + it * 4096, lo);
-                    if (a.probs != nullptr) {                    // partial linear3 products of R_k (this lane's 4 channels)
+                    if (a.probs != nullptr && !(a.dbg & 8192)) {  // partial linear3 products of R_k (this lane's 4 channels)
                         hv0 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l));
                         hv1 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l));
                         hv2 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l));
                         hv3 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l));
                     }
                 }
-                if (a.probs != nullptr) {
+                if (a.probs != nullptr && !(a.dbg & 8192)) {
                     // halving butterfly over the 16 lanes of the row: lanes 0 / 4 / 8 / 12 end with hid(R)[0 / 1 / 2 / 3]
                     const float a0 = (b3 ? hv2 : hv0) + __shfl_xor_sync(0xffffffffu, b3 ? hv0 : hv2, 8);
                     const float a1 = (b3 ? hv3 : hv1) + __shfl_xor_sync(0xffffffffu, b3 ? hv1 : hv3, 8);
@@ -1118,19 +1038,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
             process(oa, 2);
             process(ob, 3);
         }
-        }
         GN_TICK(3)
+        float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
+        if (a.probs != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
         umma::fence_proxy_async();
-        HSYNC();                                                                // S3
+        HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         GN_TICK(4)
-        // ---- P4: GEMM2 || prefetch of the next tile || softmax of the input state ; I' epilogue (+ hid(I_{k+1}))
+        // ---- P4: GEMM2 || metadata of the next tile (one thread of the idle warp 15) || softmax of the input state ;
+        //      I' epilogue (+ hid(I_{k+1}))
         if (do_g2 && t == 0) umma::issue_split_gemm80(tmem, mbar, whi, wlo, xs_addr, ls_addr);
-        const int seq_next = *seq_slot;
-        if (t == 0 && seq_next < n_tiles) prefetch_rows(nsched);
+        if (t == D_HALF - 32) fetch_meta(kfetch);
+        ++kfetch;
         if (a.probs != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
             const float4 hR = *reinterpret_cast<const float4*>(hr_s + 4 * t);
-            const float4 hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
             const float4 b3v = *reinterpret_cast<const float4*>(small);
             const float4 w2v = *reinterpret_cast<const float4*>(small + 4);
             const float b2v = small[8];
@@ -1164,18 +1085,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
             }
         }
         umma::fence_before_sync();
-        HSYNC();                                                                // S4
+        HSYNC();                                                                // S4 (the next tile's metadata is published)
         GN_TICK(5)
         // ---- P5: coalesced store of I'_{k+1}
         {
             float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (hw + 32 * i < nrows) stg4_hint(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096), pol_stream);
+                if (hw + 32 * i < nrows && !(a.dbg & 16384)) stg4_hint(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096), pol_stream);
         }
         HSYNC();                                                                // S5
         GN_TICK(6)
-        seq = seq_next;
     }
     if (a.tbuf && tid == 0)
         for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
@@ -1601,15 +1521,15 @@ static int launch_step_ws(const gnode_batch* b, const StepArgs& a, cudaStream_t 
     return GNODE_OK;
 }
 
-template <bool FAST, bool FUSED>
+template <bool FAST>
 static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     static bool configured[64] = {false};
     if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_TOTAL));
         configured[b->device & 63] = true;
     }
     const int grid = std::min((b->n_tiles + 1) / 2, b->sm_count);
-    step_dual_kernel<FAST, FUSED><<<grid, D_THREADS, D_TOTAL, stream>>>(a);
+    step_dual_kernel<FAST><<<grid, D_THREADS, D_TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;
 }
@@ -1629,9 +1549,7 @@ template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
     if (MODE == MODE_STEP && use_dual()) {
-        static const bool fused = getenv("GNODE_FUSED_ROWS") && atoi(getenv("GNODE_FUSED_ROWS")) != 0;   // experiment switch
-        if (fused) return (var & VAR_FASTSIG) ? launch_step_dual<true, true>(b, a, stream) : launch_step_dual<false, true>(b, a, stream);
-        return (var & VAR_FASTSIG) ? launch_step_dual<true, false>(b, a, stream) : launch_step_dual<false, false>(b, a, stream);
+        return (var & VAR_FASTSIG) ? launch_step_dual<true>(b, a, stream) : launch_step_dual<false>(b, a, stream);
     }
     if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 2)
         return (var & VAR_FASTSIG) ? launch_step_ws<true>(b, a, stream) : launch_step_ws<false>(b, a, stream);

@@ -211,6 +211,22 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
         GN_CUDA(cudaMalloc(&b->d_sched, sizeof(int2) * b->n_tiles));
         GN_CUDA(cudaMemcpy(b->d_sched, sched.data(), sizeof(int2) * b->n_tiles, cudaMemcpyHostToDevice));
     }
+    {   // per-tile metadata of the dual step kernel
+        std::vector<int4> tm(b->n_tiles);
+        for (int32_t t = 0; t < b->n_tiles; ++t) {
+            const int64_t r0 = (int64_t)t * TILE, r1 = std::min<int64_t>(r0 + TILE, M);
+            const int32_t ii = tile_inst[t];
+            const bool single = r1 <= (int64_t)inst[ii].row0 + inst[ii].n;
+            tm[t] = make_int4(0, 0, ii, single ? 1 : 0);
+            if (single) {
+                const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
+                tm[t].x = rp[r0 - inst[ii].row0];
+                tm[t].y = rp[r1 - inst[ii].row0] - tm[t].x;
+            }
+        }
+        GN_CUDA(cudaMalloc(&b->d_tile_meta, sizeof(int4) * b->n_tiles));
+        GN_CUDA(cudaMemcpy(b->d_tile_meta, tm.data(), sizeof(int4) * b->n_tiles, cudaMemcpyHostToDevice));
+    }
     *out = b;
     return GNODE_OK;
 }
@@ -221,6 +237,7 @@ extern "C" int gnode_batch_destroy(gnode_batch_t b) {
     cudaFree(b->d_tile_inst);
     cudaFree(b->d_tile_order);
     cudaFree(b->d_sched);
+    cudaFree(b->d_tile_meta);
     delete b;
     return GNODE_OK;
 }
