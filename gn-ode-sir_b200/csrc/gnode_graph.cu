@@ -177,20 +177,27 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
             tile_cost[t] += rp[nloc + 1] - rp[nloc];
         }
     }
-    // Processing order for the dynamic tile scheduler: tiles whose gather work exceeds 4x the mean
-    // (hub tiles of power-law graphs) are started first, heaviest first; all others keep the
-    // row-major order so that concurrently processed tiles share their trial's I' rows in L2.
+    // Processing order for the dynamic tile scheduler: instance by instance (= trial by trial, so that concurrently
+    // processed tiles share their trial's I' rows in L2), and inside an instance the tiles whose gather work exceeds
+    // 4x the mean (hub tiles of power-law graphs) first, heaviest first, then the others in row-major order.
+    // Instances smaller than a few tiles are grouped 64 at a time so that tiny graphs keep a row-major order.
     std::vector<int32_t> order;
     order.reserve(b->n_tiles);
     {
         const double mean = (double)nnz / std::max(1, b->n_tiles);
-        std::vector<int32_t> heavy;
-        for (int32_t t = 0; t < b->n_tiles; ++t)
-            if ((double)tile_cost[t] > 4.0 * mean + 1024.0) heavy.push_back(t);
-        std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t x, int32_t y) { return tile_cost[x] > tile_cost[y]; });
-        std::vector<char> is_heavy(b->n_tiles, 0);
-        for (int32_t t : heavy) { is_heavy[t] = 1; order.push_back(t); }
-        for (int32_t t = 0; t < b->n_tiles; ++t) if (!is_heavy[t]) order.push_back(t);
+        std::vector<int32_t> heavy, light;
+        auto flush = [&]() {
+            std::stable_sort(heavy.begin(), heavy.end(), [&](int32_t x, int32_t y) { return tile_cost[x] > tile_cost[y]; });
+            order.insert(order.end(), heavy.begin(), heavy.end());
+            order.insert(order.end(), light.begin(), light.end());
+            heavy.clear(); light.clear();
+        };
+        int32_t group_first_inst = 0;
+        for (int32_t t = 0; t < b->n_tiles; ++t) {
+            if (tile_inst[t] != group_first_inst && heavy.size() + light.size() >= 64) { flush(); group_first_inst = tile_inst[t]; }
+            if ((double)tile_cost[t] > 4.0 * mean + 1024.0) heavy.push_back(t); else light.push_back(t);
+        }
+        flush();
     }
     GN_CUDA(cudaGetDevice(&b->device));
     GN_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
