@@ -76,6 +76,7 @@ struct gnode_batch {
     int32_t* d_tile_order = nullptr; // [n_tiles] processing order: hub-heavy tiles first, then row-major
     int2* d_sched = nullptr;         // [n_tiles] by sequence number: {tile, first row of the look-ahead I' prefetch or -1}
     int4* d_tile_meta = nullptr;     // [n_tiles] {first CSR entry, entry count, owning instance, 1 if inside one instance}
+    int4* d_sub_meta = nullptr;      // [2 n_tiles] the same for the two 64-row halves of every tile
     int device = 0;
     int sm_count = 0;
 };
@@ -87,6 +88,7 @@ struct GnBatchView {
     const int32_t* tile_order;
     const int2* sched;
     const int4* tile_meta;
+    const int4* sub_meta;
     int32_t n_inst;
     int32_t n_tiles;
     int32_t M;
@@ -99,6 +101,7 @@ inline GnBatchView gn_view(const gnode_batch* b) {
     v.tile_order = b->d_tile_order;
     v.sched = b->d_sched;
     v.tile_meta = b->d_tile_meta;
+    v.sub_meta = b->d_sub_meta;
     v.n_inst = b->n_inst;
     v.n_tiles = b->n_tiles;
     v.M = (int32_t)b->M;

@@ -669,8 +669,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
 //     beta/gamma and S rows of a tile are all in flight together;
 //   * the gather is specialised by the exact degree (1..12 rows per round trip) and reads an all-zero row for the
 //     padding slots instead of predicating; no L2 bulk prefetch (measured: evicted before use on B200).
-constexpr int D_THREADS = 1024, D_HALF = 512;
-constexpr int D_CAP = 1536;                               // colidx entries staged per tile = 3 per thread (total smem <= 196 KB keeps 60 KB of L1)
+constexpr int D_THREADS = 1024;
 constexpr int D_WHI = 0;
 constexpr int D_WLO = umma::WB80_BYTES;
 constexpr int D_B = 2 * umma::WB80_BYTES;                 // bias [64]
@@ -679,19 +678,6 @@ constexpr int D_SMALL = D_W3 + 4 * H * 4;                 // b3[4], w2[4], b2
 constexpr int D_TSLOT = D_SMALL + 64;                     // TMEM base slot
 constexpr int D_SHARED = 43008;                           // shared part, rounded up to 1 KB (operand tiles need 1024-B alignment)
 static_assert(D_TSLOT + 16 <= D_SHARED, "shared part overflows");
-constexpr int DH_X = 0;                                   // 32 KB  A operand hi / parked neighbour sums
-constexpr int DH_L = 32768;                               // 32 KB  A operand lo / S' / I' staging
-constexpr int DH_MBAR = 65536;                            // mbarrier (8) + row-pair counter (4)
-constexpr int DH_META = DH_MBAR + 16;                     // DTileMeta of the coming tile (48 B)
-constexpr int DH_BG = DH_META + 48;                       // beta[TILE], gamma[TILE]
-constexpr int DH_RP = DH_BG + 2 * TILE * 4;               // rowptr slice [TILE + 1] (+pad)
-constexpr int DH_HS = DH_RP + 544;                        // hid(S_k) [TILE][4]
-constexpr int DH_HR = DH_HS + TILE * 16;                  // hid(R_k) [TILE][4]
-constexpr int DH_CI = DH_HR + TILE * 16;                  // colidx slice as global row ids
-constexpr int DH_BYTES = ((DH_CI + D_CAP * 4 + 1023) / 1024) * 1024;
-constexpr int D_TOTAL = D_SHARED + 2 * DH_BYTES + 1024;
-static_assert(D_TOTAL + 1024 <= 232448, "the CTA must fit in one SM's shared memory");
-
 // up to 4*NB neighbour rows of one row, all loads issued before the first add (one memory round trip)
 template <int NB>
 __device__ __forceinline__ void gather_block(float4& acc, const float* __restrict__ lane_base, const int* cp, int j0, int deg, uint64_t pol) {
@@ -773,54 +759,85 @@ struct DTileMeta {
     int inst0;
 };
 
-template <bool FAST>
+// Compile-time geometry of the pipelined step kernel: NP independent tile pipelines per CTA (2 or 4), each of PT
+// threads working on TR-row tiles (TR = UMMA M). The row-per-half-warp loops run 4 passes in both cases.
+template <int NP>
+struct PipeCfg {
+    static constexpr int PT = D_THREADS / NP;              // threads per pipeline (512 / 256)
+    static constexpr int TR = 256 / NP;                    // tile rows (128 / 64)
+    static constexpr int RSTEP = PT / 16;                  // rows per pass (32 / 16)
+    static constexpr int PASS = RSTEP * 128;               // byte offset between the passes' rows in an operand tile
+    static constexpr int CAP = 3 * PT;                     // colidx entries staged per tile (3 per thread)
+    static constexpr int KBLK = TR * 128;                  // bytes of one K-block (32 fp32) of the A operand
+    static constexpr int P_X = 0;                          // A operand hi / parked neighbour sums
+    static constexpr int P_L = 2 * KBLK;                   // A operand lo / S' / I' staging
+    static constexpr int P_MBAR = 4 * KBLK;                // mbarrier (8) + row-pair counter (4)
+    static constexpr int P_META = P_MBAR + 16;             // DTileMeta of the coming tile (48 B)
+    static constexpr int P_BG = P_META + 48;               // beta[TR], gamma[TR]
+    static constexpr int P_RP = P_BG + 2 * TR * 4;         // rowptr slice [TR + 1] (+pad)
+    static constexpr int P_HS = P_RP + TR * 4 + 32;        // hid(S_k) [TR][4]
+    static constexpr int P_HR = P_HS + TR * 16;            // hid(R_k) [TR][4]
+    static constexpr int P_CI = P_HR + TR * 16;            // colidx slice (instance-local ids) + 64 B over-read pad
+    static constexpr int P_BYTES = ((P_CI + CAP * 4 + 64 + 1023) / 1024) * 1024;
+    static constexpr int TOTAL = D_SHARED + NP * P_BYTES + 1024;
+    static constexpr int TMEM_COLS = 128 * NP;             // one [TR x 80] accumulator per pipeline, 128 columns apart
+    static_assert(TOTAL + 1024 <= 200704, "stay inside the 196 KB shared-memory carve-out (60 KB of L1 left)");
+    static_assert(PT / 4 >= TR, "beta / gamma staging needs a quarter of the pipeline's threads per array");
+    // byte offset of the 16-byte chunk c4 of tile row r (canonical UMMA K-major SWIZZLE_128B, two K-blocks)
+    static __device__ __forceinline__ int sw(int r, int c4) { return (c4 >> 3) * KBLK + (r << 7) + (((c4 & 7) ^ (r & 7)) << 4); }
+};
+
+template <bool FAST, int NP>
 __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs a) {
+    using C = PipeCfg<NP>;
+    constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x;
-    const int half = __shfl_sync(0xffffffffu, tid >> 9, 0);          // provably warp-uniform
-    const int t = tid & (D_HALF - 1), lane = t & 31;
+    const int half = __shfl_sync(0xffffffffu, tid / PT, 0);          // pipeline index, provably warp-uniform
+    const int t = tid & (PT - 1), lane = t & 31;
     const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);            // warp index inside the half
     const int l = t & 15, hw = t >> 4;
-    unsigned char* hb = smem + D_SHARED + half * DH_BYTES;
-    unsigned char* Xs = hb + DH_X;
-    unsigned char* Ls = hb + DH_L;
+    unsigned char* hb = smem + D_SHARED + half * C::P_BYTES;
+    unsigned char* Xs = hb + C::P_X;
+    unsigned char* Ls = hb + C::P_L;
     float* bs = reinterpret_cast<float*>(smem + D_B);
     float* W3s = reinterpret_cast<float*>(smem + D_W3);
     float* small = reinterpret_cast<float*>(smem + D_SMALL);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + D_TSLOT);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(hb + DH_MBAR);
-    int* row_ctr = reinterpret_cast<int*>(hb + DH_MBAR + 8);
-    DTileMeta* meta = reinterpret_cast<DTileMeta*>(hb + DH_META);
-    float* bg_s = reinterpret_cast<float*>(hb + DH_BG);
-    int* rp_s = reinterpret_cast<int*>(hb + DH_RP);
-    float* hs_s = reinterpret_cast<float*>(hb + DH_HS);
-    float* hr_s = reinterpret_cast<float*>(hb + DH_HR);
-    int* ci_s = reinterpret_cast<int*>(hb + DH_CI);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(hb + C::P_MBAR);
+    int* row_ctr = reinterpret_cast<int*>(hb + C::P_MBAR + 8);
+    DTileMeta* meta = reinterpret_cast<DTileMeta*>(hb + C::P_META);
+    float* bg_s = reinterpret_cast<float*>(hb + C::P_BG);
+    int* rp_s = reinterpret_cast<int*>(hb + C::P_RP);
+    float* hs_s = reinterpret_cast<float*>(hb + C::P_HS);
+    float* hr_s = reinterpret_cast<float*>(hb + C::P_HR);
+    int* ci_s = reinterpret_cast<int*>(hb + C::P_CI);
     const int bar_id = 1 + half;
-#define HSYNC() umma::bar_sync(bar_id, D_HALF)
+#define HSYNC() umma::bar_sync(bar_id, PT)
 
     const int M = a.bv.M;
     const size_t plane = (size_t)M * H;
-    const int n_tiles = a.bv.n_tiles;
-    const int off0 = sw_off(hw, l);
+    const int n_tiles = (NP == 2 ? 1 : 2) * a.bv.n_tiles;          // units of TR rows
+    const int off0 = C::sw(hw, l);
     // timing experiments: GNODE_DBG bit 8 (256) = gathered rows without evict_last, bit 9 (512) = streams without evict_first
     const uint64_t pol_keep = (a.dbg & 256) ? l2_policy_evict_normal() : l2_policy_evict_last();
     const uint64_t pol_stream = (a.dbg & 512) ? l2_policy_evict_normal() : l2_policy_evict_first();
 
     // one thread: draw the next sequence number and resolve its metadata (3 dependent loads of small tables)
     auto fetch_meta = [&](int k) {
-        int seq = a.counter ? atomicAdd(a.counter, 1) : 2 * (int)blockIdx.x + half + 2 * k * (int)gridDim.x;
-        if ((a.dbg & 2048) && half == 1) seq = n_tiles;               // timing experiment: one pipeline per SM
+        int seq = a.counter ? atomicAdd(a.counter, 1) : NP * (int)blockIdx.x + half + NP * k * (int)gridDim.x;
+        if ((a.dbg & 2048) && half != 0) seq = n_tiles;               // timing experiment: one pipeline per SM
         DTileMeta m;
         m.seq = seq; m.rowptr = nullptr; m.colidx = nullptr;
         m.tile0 = 0; m.nrows = 0; m.i_row0 = 0; m.single = 0; m.ebase = 0; m.ecnt = 0; m.inst0 = 0;
         if (seq < n_tiles) {
-            const int tile = a.bv.tile_order[seq];
-            const int4 tm = a.bv.tile_meta[tile];                     // {ebase, ecnt, inst0, single}
+            // NP == 4: the 128-row tiles of the batch tables are processed as two 64-row halves
+            const int tile = a.bv.tile_order[NP == 2 ? seq : (seq >> 1)];
+            const int4 tm = NP == 2 ? a.bv.tile_meta[tile] : a.bv.sub_meta[2 * tile + (seq & 1)];   // {ebase, ecnt, inst0, single}
             const GnInstance I = a.bv.inst[tm.z];
-            m.tile0 = tile * TILE;
-            m.nrows = min(TILE, M - m.tile0);
+            m.tile0 = tile * TILE + (NP == 2 ? 0 : (seq & 1) * TR);
+            m.nrows = max(0, min(TR, M - m.tile0));
             m.i_row0 = I.row0; m.single = tm.w; m.ebase = tm.x; m.ecnt = tm.y; m.inst0 = tm.z;
             m.rowptr = I.rowptr + (m.tile0 - I.row0);
             m.colidx = I.colidx;
@@ -829,7 +846,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
     };
 
     umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
-    if (tid < 32) umma::tmem_alloc(tslot, 256);
+    if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
     if (t == 0) { umma::mbar_init(mbar, 1); fetch_meta(0); }
     umma::fence_before_sync();
     if (tid < H) bs[tid] = a.p.lin_b[tid];
@@ -838,11 +855,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
     if (tid == 0) small[8] = a.p.s2_b[0];
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = *tslot + (uint32_t)half * 128u;             // this half's [128 x 80] fp32 accumulator
+    const uint32_t tmem = *tslot + (uint32_t)half * 128u;             // this pipeline's [TR x 80] fp32 accumulator
     const uint32_t whi = umma::smem_u32(smem + D_WHI), wlo = umma::smem_u32(smem + D_WLO);
     const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
-    const int q = warp & 3, cq = warp >> 2;                           // TMEM lane quarter / 16-column block of this warp
-    const int erow = q * 32 + lane;                                   // tile row this thread owns in the epilogues
+    // epilogue geometry. TR = 128: 16 warps = 4 TMEM lane quarters x 4 blocks of 16 columns, lane == tile row.
+    // TR = 64 (measured with tools/umma_m64_probe.cu): rows 16q .. 16q+15 live in lanes 0..15 of quarter q, so 8 warps =
+    // 4 quarters x 2 halves of 32 columns, and only lanes 0..15 hold rows.
+    const int q = warp & 3, cq = warp >> 2;
+    constexpr int NCB = (NP == 2) ? 1 : 2;                            // 16-column blocks per warp
+    const bool erow_ok = (NP == 2) || lane < 16;
+    const int erow = q * (TR / 4) + lane;                             // tile row this thread owns in the epilogues
     uint32_t phase = 0;
     int kfetch = 1;
 
@@ -852,7 +874,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            sreg[i] = (hw + 32 * i < nrows) ? ldg4_hint(src + (size_t)i * 32 * H, pol_stream) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sreg[i] = (hw + RSTEP * i < nrows) ? ldg4_hint(src + (size_t)i * RSTEP * H, pol_stream) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
@@ -869,53 +891,57 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
             load_s(tile0, nrows);
             int rpv = 0, civ[3] = {0, 0, 0};
             float bgv = 0.f;
-            const int ecnt = min(m.ecnt, D_CAP);
+            const int ecnt = min(m.ecnt, C::CAP);
             if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
             if (single) {
 #pragma unroll
-                for (int u = 0; u < 3; ++u) if (t + u * D_HALF < ecnt) civ[u] = __ldg(m.colidx + ebase + t + u * D_HALF);
+                for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) civ[u] = __ldg(m.colidx + ebase + t + u * PT);
             }
-            if (t >= 256 && t < 256 + nrows) bgv = a.beta[tile0 + t - 256];
-            if (t >= 384 && t < 384 + nrows) bgv = a.gamma[tile0 + t - 384];
+            if (t >= PT / 2 && t < PT / 2 + nrows) bgv = a.beta[tile0 + t - PT / 2];
+            if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float4 hi, lo;
                 umma::tf32_split4(sreg[i], hi, lo);
-                sts4(Xs, off0 + i * 4096, hi);
-                sts4(Ls, off0 + i * 4096, lo);
+                sts4(Xs, off0 + i * PASS, hi);
+                sts4(Ls, off0 + i * PASS, lo);
             }
             umma::fence_proxy_async();
             if (t == 0) *row_ctr = 0;
             if (single && t <= nrows) rp_s[t] = rpv;
             if (single) {
 #pragma unroll
-                for (int u = 0; u < 3; ++u) if (t + u * D_HALF < ecnt) ci_s[t + u * D_HALF] = civ[u];   // instance-local ids
+                for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = civ[u];   // instance-local ids
             }
-            if (t >= 256 && t < 256 + nrows) bg_s[t - 256] = bgv;
-            if (t >= 384 && t < 384 + nrows) bg_s[TILE + t - 384] = bgv;
+            if (t >= PT / 2 && t < PT / 2 + nrows) bg_s[t - PT / 2] = bgv;
+            if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bg_s[TR + t - 3 * PT / 4] = bgv;
         }
         HSYNC();                                                                // S1
         GN_TICK(0)
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         const bool do_g1 = !(a.dbg & 16), do_g2 = !(a.dbg & 8);       // timing experiments only
-        if (do_g1 && t == 0) umma::issue_split_gemm80(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (do_g1 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
         if (do_g1) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }        // hardware-suspended wait (no spinning)
         umma::fence_after_sync();
         if (do_g1) {
-            float v[16];
-            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
-                float4 o;
-                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
-                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
-                sts4(Ls, sw_off(erow, 4 * cq + j), o);
+            for (int cb = 0; cb < NCB; ++cb) {
+                const int c16 = NCB * cq + cb;                        // 16-column block
+                float v[16];
+                umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * c16, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c16 + 4 * j);
+                    float4 o;
+                    o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                    o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                    if (erow_ok) sts4(Ls, C::sw(erow, 4 * c16 + j), o);
+                }
             }
             if (cq == 0) {
                 float hv[4];
                 umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
-                *reinterpret_cast<float4*>(hs_s + 4 * erow) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                if (erow_ok) *reinterpret_cast<float4*>(hs_s + 4 * erow) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
         }
         umma::fence_before_sync();
@@ -930,26 +956,26 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                 int p = 0;
                 if (lane == 0) p = atomicAdd(row_ctr, 1);
                 p = __shfl_sync(0xffffffffu, p, 0);
-                while (p < TILE / 2) {
+                while (p < TR / 2) {
                     int pn = 0;
                     if (lane == 0) pn = atomicAdd(row_ctr, 1);
                     const int rr = 2 * p + (lane >> 4);
                     int e_rel = 0, deg = 0;
                     if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
-                    const int over = (e_rel + deg > D_CAP) ? 1 : 0;
+                    const int over = (e_rel + deg > C::CAP) ? 1 : 0;
                     float4 acc;
                     if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
                         acc = gather_smem_z(lane_base, m.colidx + ebase + e_rel, deg, zrow, pol_keep);
                     else
                         acc = gather_smem_z(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
-                    sts4(Xs, sw_off(rr, l), acc);
+                    sts4(Xs, C::sw(rr, l), acc);
                     p = __shfl_sync(0xffffffffu, pn, 0);
                 }
             } else {                                         // tile spans several (small) instances
                 int inst = m.inst0;
 #pragma unroll 1
-                for (int it = 0; it < TILE / 32; ++it) {
-                    const int rr = hw + 32 * it;
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = hw + RSTEP * it;
                     int row0 = 0, e0 = 0, deg = 0;
                     const int32_t* ci = nullptr;
                     if (rr < nrows) {
@@ -961,7 +987,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                         deg = I.rowptr[g - row0 + 1] - e0;
                     }
                     const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
-                    sts4(Xs, off0 + it * 4096, acc);
+                    sts4(Xs, off0 + it * PASS, acc);
                 }
             }
         }
@@ -972,7 +998,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         {
             struct Own { float4 s, iv, rv, ipo; };
             auto load_own = [&](Own& o, int it) {
-                const int rr = hw + 32 * it;
+                const int rr = hw + RSTEP * it;
                 o.s = make_float4(1.f, 1.f, 1.f, 1.f); o.iv = o.s; o.rv = o.s; o.ipo = o.s;
                 if (rr < nrows && !(a.dbg & 4)) {
                     const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
@@ -984,14 +1010,14 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
             };
             const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
             auto process = [&](const Own& o, int it) {
-                const int rr = hw + 32 * it;
+                const int rr = hw + RSTEP * it;
                 const bool valid = rr < nrows;
                 float hv0 = 0.f, hv1 = 0.f, hv2 = 0.f, hv3 = 0.f;
                 if (valid) {
                     const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                    const float4 acc = lds4(Xs, off0 + it * 4096);
-                    const float4 sp = lds4(Ls, off0 + it * 4096);
-                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
+                    const float4 acc = lds4(Xs, off0 + it * PASS);
+                    const float4 sp = lds4(Ls, off0 + it * PASS);
+                    const float nbe = -bg_s[rr], ga = bg_s[TR + rr], dt = a.dt;
                     float4 sn, in_, rn;
 #define GN_COMP(c)                                                                  \
     {                                                                               \
@@ -1011,8 +1037,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                     }
                     float4 hi, lo;
                     umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
-                    sts4(Xs, off0 + it * 4096, hi);
-                    sts4(Ls, off0 + it * 4096, lo);
+                    sts4(Xs, off0 + it * PASS, hi);
+                    sts4(Ls, off0 + it * PASS, lo);
                     if (a.probs != nullptr && !(a.dbg & 8192)) {  // partial linear3 products of R_k (this lane's 4 channels)
                         hv0 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l));
                         hv1 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l));
@@ -1046,8 +1072,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         GN_TICK(4)
         // ---- P4: GEMM2 || metadata of the next tile (one thread of the idle warp 15) || softmax of the input state ;
         //      I' epilogue (+ hid(I_{k+1}))
-        if (do_g2 && t == 0) umma::issue_split_gemm80(tmem, mbar, whi, wlo, xs_addr, ls_addr);
-        if (t == D_HALF - 32) fetch_meta(kfetch);
+        if (do_g2 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
         if (a.probs != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
@@ -1068,20 +1094,24 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         if (do_g2) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }
         umma::fence_after_sync();
         if (do_g2) {
-            float v[16];
-            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
-                float4 o;
-                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
-                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
-                sts4(Ls, sw_off(erow, 4 * cq + j), o);
+            for (int cb = 0; cb < NCB; ++cb) {
+                const int c16 = NCB * cq + cb;                        // 16-column block
+                float v[16];
+                umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * c16, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c16 + 4 * j);
+                    float4 o;
+                    o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                    o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                    if (erow_ok) sts4(Ls, C::sw(erow, 4 * c16 + j), o);
+                }
             }
             if (cq == 0) {
                 float hv[4];
                 umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
-                if (erow < nrows) *reinterpret_cast<float4*>(a.hid_i + (size_t)(tile0 + erow) * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                if (erow_ok && erow < nrows) *reinterpret_cast<float4*>(a.hid_i + (size_t)(tile0 + erow) * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
         }
         umma::fence_before_sync();
@@ -1092,7 +1122,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
             float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (hw + 32 * i < nrows && !(a.dbg & 16384)) stg4_hint(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096), pol_stream);
+                if (hw + RSTEP * i < nrows && !(a.dbg & 16384)) stg4_hint(dst + (size_t)i * RSTEP * H, lds4(Ls, off0 + i * PASS), pol_stream);
         }
         HSYNC();                                                                // S5
         GN_TICK(6)
@@ -1103,7 +1133,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
 #undef HSYNC
     umma::fence_before_sync();
     __syncthreads();
-    if (tid < 32) umma::tmem_dealloc(*tslot, 256);
+    if (tid < 32) umma::tmem_dealloc(*tslot, C::TMEM_COLS);
 }
 
 // Decoder + softmax of one stored state (the last grid point of the dual-kernel rollout): probs = softmax over
@@ -1521,35 +1551,37 @@ static int launch_step_ws(const gnode_batch* b, const StepArgs& a, cudaStream_t 
     return GNODE_OK;
 }
 
-template <bool FAST>
+template <bool FAST, int NP>
 static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     static bool configured[64] = {false};
     if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
         configured[b->device & 63] = true;
     }
-    const int grid = std::min((b->n_tiles + 1) / 2, b->sm_count);
-    step_dual_kernel<FAST><<<grid, D_THREADS, D_TOTAL, stream>>>(a);
+    const int units = (NP == 2 ? 1 : 2) * b->n_tiles;
+    const int grid = std::min((units + NP - 1) / NP, b->sm_count);
+    step_dual_kernel<FAST, NP><<<grid, D_THREADS, PipeCfg<NP>::TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;
 }
 
-// 3 = dual (default: two tile pipelines per CTA, decoder hidden layer on the tensor core), 1 = phase-structured,
-// 2 = warp-specialised, 0 = generic
+// 3 = pipelined, 2 x 128-row tile pipelines per CTA (default; decoder hidden layer on the tensor core), 4 = the same
+// kernel with 4 x 64-row pipelines, 1 = phase-structured, 2 = warp-specialised, 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? (atoi(e) & 3) : 3; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 4) : 3; }
     return g_step_kernel;
 }
 
 // the dual kernel emits probs[k] of its INPUT state and needs the hid_i side buffer (tensor-core variants only)
-static bool use_dual() { return (current_variant() & VAR_TC) && step_kernel_choice() == 3; }
+static bool use_dual() { return (current_variant() & VAR_TC) && step_kernel_choice() >= 3; }
 
 template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
     if (MODE == MODE_STEP && use_dual()) {
-        return (var & VAR_FASTSIG) ? launch_step_dual<true>(b, a, stream) : launch_step_dual<false>(b, a, stream);
+        if (step_kernel_choice() == 4) return (var & VAR_FASTSIG) ? launch_step_dual<true, 4>(b, a, stream) : launch_step_dual<false, 4>(b, a, stream);
+        return (var & VAR_FASTSIG) ? launch_step_dual<true, 2>(b, a, stream) : launch_step_dual<false, 2>(b, a, stream);
     }
     if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 2)
         return (var & VAR_FASTSIG) ? launch_step_ws<true>(b, a, stream) : launch_step_ws<false>(b, a, stream);
@@ -1576,7 +1608,7 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
-    if (kernel < 0 || kernel > 3) { set_error("gnode_set_step_kernel: kernel must be 0..3"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 4) { set_error("gnode_set_step_kernel: kernel must be 0..4"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }

@@ -218,21 +218,31 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
         GN_CUDA(cudaMalloc(&b->d_sched, sizeof(int2) * b->n_tiles));
         GN_CUDA(cudaMemcpy(b->d_sched, sched.data(), sizeof(int2) * b->n_tiles, cudaMemcpyHostToDevice));
     }
-    {   // per-tile metadata of the dual step kernel
-        std::vector<int4> tm(b->n_tiles);
-        for (int32_t t = 0; t < b->n_tiles; ++t) {
-            const int64_t r0 = (int64_t)t * TILE, r1 = std::min<int64_t>(r0 + TILE, M);
-            const int32_t ii = tile_inst[t];
-            const bool single = r1 <= (int64_t)inst[ii].row0 + inst[ii].n;
-            tm[t] = make_int4(0, 0, ii, single ? 1 : 0);
-            if (single) {
-                const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
-                tm[t].x = rp[r0 - inst[ii].row0];
-                tm[t].y = rp[r1 - inst[ii].row0] - tm[t].x;
+    {   // per-tile metadata of the pipelined step kernel, for 128-row tiles and for their 64-row halves
+        auto build = [&](int rows, std::vector<int4>& tm) {
+            const int64_t n = (M + rows - 1) / rows;
+            int32_t ii = 0;
+            for (int64_t u = 0; u < (int64_t)tm.size(); ++u) {
+                tm[u] = make_int4(0, 0, 0, 0);
+                if (u >= n) continue;                                  // second half of a partial last tile: empty
+                const int64_t r0 = u * rows, r1 = std::min<int64_t>(r0 + rows, M);
+                while (ii + 1 < n_inst && inst[ii + 1].row0 <= r0) ++ii;
+                const bool single = r1 <= (int64_t)inst[ii].row0 + inst[ii].n;
+                tm[u].z = ii; tm[u].w = single ? 1 : 0;
+                if (single) {
+                    const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
+                    tm[u].x = rp[r0 - inst[ii].row0];
+                    tm[u].y = rp[r1 - inst[ii].row0] - tm[u].x;
+                }
             }
-        }
-        GN_CUDA(cudaMalloc(&b->d_tile_meta, sizeof(int4) * b->n_tiles));
-        GN_CUDA(cudaMemcpy(b->d_tile_meta, tm.data(), sizeof(int4) * b->n_tiles, cudaMemcpyHostToDevice));
+        };
+        std::vector<int4> tm(b->n_tiles), sm(2 * (size_t)b->n_tiles);
+        build(TILE, tm);
+        build(TILE / 2, sm);
+        GN_CUDA(cudaMalloc(&b->d_tile_meta, sizeof(int4) * tm.size()));
+        GN_CUDA(cudaMemcpy(b->d_tile_meta, tm.data(), sizeof(int4) * tm.size(), cudaMemcpyHostToDevice));
+        GN_CUDA(cudaMalloc(&b->d_sub_meta, sizeof(int4) * sm.size()));
+        GN_CUDA(cudaMemcpy(b->d_sub_meta, sm.data(), sizeof(int4) * sm.size(), cudaMemcpyHostToDevice));
     }
     *out = b;
     return GNODE_OK;
@@ -245,6 +255,7 @@ extern "C" int gnode_batch_destroy(gnode_batch_t b) {
     cudaFree(b->d_tile_order);
     cudaFree(b->d_sched);
     cudaFree(b->d_tile_meta);
+    cudaFree(b->d_sub_meta);
     delete b;
     return GNODE_OK;
 }

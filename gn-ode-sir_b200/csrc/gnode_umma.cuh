@@ -193,10 +193,12 @@ __device__ __forceinline__ void prepare_weights80(const float* __restrict__ W, c
     fence_proxy_async();
 }
 
-// One thread: D[128 x 80] (TMEM columns tmem .. tmem+79) = X [W; W3]^T as the 4-term split product, then commit.
+// One thread: D[TR x 80] (TMEM columns tmem .. tmem+79) = X [W; W3]^T as the 4-term split product, then commit.
+// TR = UMMA M = 128 or 64; the A operand's K-block stride is TR * 128 B.
+template <int TR>
 __device__ __forceinline__ void issue_split_gemm80(uint32_t tmem, uint64_t* bar, uint32_t whi, uint32_t wlo, uint32_t xhi, uint32_t xlo) {
     fence_after_sync();
-    constexpr uint32_t idesc = instr_desc_tf32(TILE, NB80);
+    constexpr uint32_t idesc = instr_desc_tf32(TR, NB80);
     uint32_t acc = 0;
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
@@ -204,7 +206,7 @@ __device__ __forceinline__ void issue_split_gemm80(uint32_t tmem, uint64_t* bar,
         const uint32_t bbase = (pass == 0 || pass == 2) ? wlo : whi;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t aoff = ((k >> 2) << 14) + ((k & 3) << 5);
+            const uint32_t aoff = (uint32_t)(k >> 2) * (TR * 128) + ((k & 3) << 5);
             const uint32_t boff = (uint32_t)(k >> 2) * WB80_KBLOCK + ((k & 3) << 5);
             mma_tf32(tmem, smem_desc(abase + aoff), smem_desc(bbase + boff), idesc, acc);
             acc = 1;

@@ -76,10 +76,11 @@ int gnode_version(void);
  * bit 1 = MUFU ex2/rcp sigmoid (else expf + IEEE division). Default: env GNODE_VARIANT or the build default. */
 int gnode_set_variant(int variant);
 int gnode_get_variant(void);
-/* Structure of the tensor-core step kernel (variants with bit 0 set): 3 = dual (default: one 1024-thread CTA per SM
- * running two tile pipelines that share the weight operand; the decoder's hidden layer comes out of the step's two
- * GEMMs), 1 = phase-structured (two 512-thread CTAs per SM), 2 = warp-specialised, 0 = generic. Default: env
- * GNODE_STEP_KERNEL or 3. All produce the same trajectories within the parity tolerance. */
+/* Structure of the tensor-core step kernel (variants with bit 0 set): 3 = pipelined (default: one 1024-thread CTA per
+ * SM running two 128-row tile pipelines that share the weight operand; the decoder's hidden layer comes out of the
+ * step's two GEMMs), 4 = the same kernel with four 64-row pipelines, 1 = phase-structured (two 512-thread CTAs per
+ * SM), 2 = warp-specialised, 0 = generic. Default: env GNODE_STEP_KERNEL or 3. All produce the same trajectories
+ * within the parity tolerance. */
 int gnode_set_step_kernel(int kernel);
 int gnode_get_step_kernel(void);
 /* debug: per-phase SM-cycle sums of the step kernel collected while env GNODE_DBG has bit 7 set; resets them */

@@ -71,7 +71,7 @@ def test_variant_large_graph_fp64(gn, variant):
     assert err_ours <= max(1e-5, 2.0 * err_ref), (err_ours, err_ref)
 
 
-STEP_KERNELS = {3: "dual", 1: "phase", 2: "warp-specialised", 0: "generic"}
+STEP_KERNELS = {3: "dual", 4: "quad", 1: "phase", 2: "warp-specialised", 0: "generic"}
 
 
 @pytest.fixture
@@ -104,13 +104,14 @@ def test_step_kernels_agree_on_training_trajectory(gn):
     prev = L.gnode_get_step_kernel()
     out = {}
     try:
-        for k in (3, 1):
+        for k in (3, 4, 1):
             _lib.check(L.gnode_set_step_kernel(k), "gnode_set_step_kernel")
             ps = [p.requires_grad_() for p in dev_params(g.params)]
             dt = gn.rollout.dt_array(orc.time_grid(g.maxTime, g.deltaT))
             out[k] = gn.rollout.rollout(g.x.to(DEV), make_batch(gn, g), dt, ps).detach().cpu()
     finally:
         L.gnode_set_step_kernel(prev)
-    err = (out[3] - out[1]).abs().max().item()
-    print("dual vs phase (training forward): %.3e" % err)
-    assert err < 2e-6, err
+    for k in (3, 4):
+        err = (out[k] - out[1]).abs().max().item()
+        print("step kernel %d vs phase (training forward): %.3e" % (k, err))
+        assert err < 2e-6, err
