@@ -993,23 +993,29 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
         }
         HSYNC();                                                                // S2b: every AI row is parked
         GN_TICK(2)
-        // ---- P3b: SIR update, stores; hid(R_k) -> smem; I_{k+1} hi/lo -> operand tiles. Two own-row register sets:
-        //      the loads of rows it and it+1 are in flight together (two exposed memory round trips per tile, not four).
+        // ---- P3b: SIR update, stores; hid(R_k) -> smem; I_{k+1} hi/lo -> operand tiles. The lane's 4 x 4 linear3
+        //      weights stay in registers for the four passes (the kernel is bound by LSU wavefronts: re-reading them
+        //      from shared memory per row cost 8 of the 55 shared-memory wavefronts per row).
         {
-            struct Own { float4 s, iv, rv, ipo; };
-            auto load_own = [&](Own& o, int it) {
+            float4 s, iv, rv, ipo;
+            auto load_own = [&](int it) {
                 const int rr = hw + RSTEP * it;
-                o.s = make_float4(1.f, 1.f, 1.f, 1.f); o.iv = o.s; o.rv = o.s; o.ipo = o.s;
+                s = make_float4(1.f, 1.f, 1.f, 1.f); iv = s; rv = s; ipo = s;
                 if (rr < nrows && !(a.dbg & 4)) {
                     const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                    o.s = ldg4_hint(a.y_in + off, pol_stream);
-                    o.iv = ldg4_hint(a.y_in + plane + off, pol_stream);
-                    o.rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
-                    o.ipo = ldg4_hint(a.ip_in + off, pol_keep);
+                    s = ldg4_hint(a.y_in + off, pol_stream);
+                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
+                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
+                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
                 }
             };
+            load_own(0);
+            const bool dec = a.probs != nullptr && !(a.dbg & 8192);
             const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
-            auto process = [&](const Own& o, int it) {
+            const float4 w30 = *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l), w31 = *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l),
+                         w32 = *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l), w33 = *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l);
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
                 const int rr = hw + RSTEP * it;
                 const bool valid = rr < nrows;
                 float hv0 = 0.f, hv1 = 0.f, hv2 = 0.f, hv3 = 0.f;
@@ -1022,11 +1028,11 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
 #define GN_COMP(c)                                                                  \
     {                                                                               \
         const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
-        const float dR = __fmul_rn(ga, o.ipo.c);                                    \
+        const float dR = __fmul_rn(ga, ipo.c);                                      \
         const float dI = __fsub_rn(-dS, dR);                                        \
-        sn.c = __fadd_rn(o.s.c, __fmul_rn(dt, dS));                                 \
-        in_.c = __fadd_rn(o.iv.c, __fmul_rn(dt, dI));                               \
-        rn.c = __fadd_rn(o.rv.c, __fmul_rn(dt, dR));                                \
+        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
+        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
+        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
     }
                     GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
 #undef GN_COMP
@@ -1039,14 +1045,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                     umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
                     sts4(Xs, off0 + it * PASS, hi);
                     sts4(Ls, off0 + it * PASS, lo);
-                    if (a.probs != nullptr && !(a.dbg & 8192)) {  // partial linear3 products of R_k (this lane's 4 channels)
-                        hv0 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l));
-                        hv1 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l));
-                        hv2 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l));
-                        hv3 = dot4(o.rv, *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l));
+                    if (dec) {                                   // partial linear3 products of R_k (this lane's 4 channels)
+                        hv0 = dot4(rv, w30); hv1 = dot4(rv, w31); hv2 = dot4(rv, w32); hv3 = dot4(rv, w33);
                     }
                 }
-                if (a.probs != nullptr && !(a.dbg & 8192)) {
+                if (it + 1 < 4) load_own(it + 1);
+                if (dec) {
                     // halving butterfly over the 16 lanes of the row: lanes 0 / 4 / 8 / 12 end with hid(R)[0 / 1 / 2 / 3]
                     const float a0 = (b3 ? hv2 : hv0) + __shfl_xor_sync(0xffffffffu, b3 ? hv0 : hv2, 8);
                     const float a1 = (b3 ? hv3 : hv1) + __shfl_xor_sync(0xffffffffu, b3 ? hv1 : hv3, 8);
@@ -1055,14 +1059,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
                     c += __shfl_xor_sync(0xffffffffu, c, 1);
                     if (valid && (l & 3) == 0) hr_s[4 * rr + (l >> 2)] = c;
                 }
-            };
-            Own oa, ob;
-            load_own(oa, 0); load_own(ob, 1);
-            process(oa, 0);
-            process(ob, 1);
-            load_own(oa, 2); load_own(ob, 3);
-            process(oa, 2);
-            process(ob, 3);
+            }
         }
         GN_TICK(3)
         float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier

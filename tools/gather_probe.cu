@@ -72,9 +72,10 @@ struct Args {
 };
 
 // ------------------------------------------------------------------ (a) LDG gather
-template <int BATCH, int MINB, int NA = 0>
+template <int BATCH, int MINB, int NA = 0, int NSM = 0>
 __global__ void __launch_bounds__(512, MINB) gather_ldg(const Args a) {
     __shared__ int tile_s;
+    __shared__ float4 pad_s[NSM > 0 ? 512 : 1];
     extern __shared__ unsigned char dyn_smem[];
     if (a.skel == 77) dyn_smem[threadIdx.x] = 1;      // keep the dynamic allocation alive
     const int tid = threadIdx.x, lane = tid & 31, l = tid & 15, hw = tid >> 4;
@@ -115,6 +116,17 @@ __global__ void __launch_bounds__(512, MINB) gather_ldg(const Args a) {
                 for (int k = 0; k < BATCH; ++k) v[k] = (c[k] >= 0) ? (NA ? ldg4_na(lane_base + (size_t)c[k] * H, keep) : ldg4_hint(lane_base + (size_t)c[k] * H, keep)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < BATCH; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+            }
+            if (NSM > 0) {          // extra shared-memory wavefronts: NSM 128-bit accesses per row (LSU pipe pressure test)
+                volatile float4* ps = pad_s;
+#pragma unroll
+                for (int i = 0; i < NSM; i += 2) {
+                    ps[tid].x = acc.x + (float)i;
+                    acc.y += ps[tid ^ 16].x * 1e-30f;
+                }
+                float4 tmp; tmp.x = acc.x; tmp.y = acc.y; tmp.z = acc.z; tmp.w = acc.w;
+                for (int i = 0; i < NSM; i += 2) { *(float4*)&pad_s[tid] = tmp; __syncwarp(); tmp = *(float4*)&pad_s[tid ^ 1]; __syncwarp(); }
+                acc.z += tmp.z * 1e-30f;
             }
             if (rr < nrows) {
                 if (a.skel) {
@@ -419,6 +431,9 @@ int main(int argc, char** argv) {
             timeit(gather_ldg<8, 2>, 2 * sms, "b8 2CTA dynsmem 64K", 65536);
             timeit(gather_ldg<8, 2>, 2 * sms, "b8 2CTA dynsmem 96K", 98304);
             timeit(gather_ldg<8, 2>, 2 * sms, "b8 2CTA dynsmem 110K", 112640);
+            timeit(gather_ldg<8, 2, 0, 8>, 2 * sms, "b8 2CTA dynsmem 96K + 16 smem wf/row", 98304);
+            timeit(gather_ldg<8, 2, 0, 16>, 2 * sms, "b8 2CTA dynsmem 96K + 32 smem wf/row", 98304);
+            timeit(gather_ldg<8, 2, 0, 28>, 2 * sms, "b8 2CTA dynsmem 96K + 56 smem wf/row", 98304);
             timeit(gather_ldg<8, 2, 1>, 2 * sms, "b8 2CTA noalloc dynsmem 0", 0);
             timeit(gather_ldg<8, 2, 1>, 2 * sms, "b8 2CTA noalloc dynsmem 110K", 112640);
             CK(cudaMemset(d_cnt, 0, 4));
