@@ -103,10 +103,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_workload(trials, trial_offset):
+WORKLOADS = {
+    "epinions": ("epinions stand-in BA(N=75879,m=5,seed=0)", "BASELINE.json configs[3]"),
+    "ba2m": ("BA(N=2000000,m=10,seed=0) stress graph (chunked preferential attachment, ~20M edges)", "BASELINE.json configs[4]"),
+}
+
+
+def build_workload(trials, trial_offset, workload="epinions"):
     from gn_ode_sir_b200 import synth
     from oracle import gnode_oracle as orc      # only for the shared synthetic-input recipe
-    A = synth.epinions_standin(seed=0)
+    A = synth.epinions_standin(seed=0) if workload == "epinions" else synth.ba_stress(seed=0)
     N = A.shape[0]
     x = torch.zeros(trials, N, 3 + H, dtype=torch.float32)
     for b in range(trials):
@@ -149,7 +155,7 @@ def cpu_reference_sample(A, orc, trials, n_points, repeats=1):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    A, _, orc = build_workload(0, 0)
+    A, _, orc = build_workload(0, 0, args.workload)
     for _ in range(args.warmup):
         cpu_reference_sample(A, orc, 1, 3)
     vals, times = [], []
@@ -170,9 +176,10 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(args, world):
-    return {"workload": "epinions stand-in BA(N=75879,m=5,seed=0) rollout inference, H=64, T=40 (maxTime=20, deltaT=0.5), "
-                        "%d trials per GPU (BASELINE.json configs[3])" % args.trials,
-            "trials_per_gpu": args.trials, "global_trials": args.trials * world, "nodes": 75879,
+    name, cfg = WORKLOADS[args.workload]
+    return {"workload": "%s rollout inference, H=64, T=40 (maxTime=20, deltaT=0.5), %d trials per GPU (%s)" % (name, args.trials, cfg),
+            "trials_per_gpu": args.trials, "global_trials": args.trials * world,
+            "nodes": 75879 if args.workload == "epinions" else 2000000,
             "euler_steps": int(len(np.arange(0, MAXTIME, DELTAT)) - 1), "parallelism": "trial-sharded dp%d, graph replicated" % world,
             "l2_policy": "no flush: per-step working set (state+I' of all trials, >3 GB) exceeds the 126 MB L2"}
 
@@ -184,6 +191,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trials", type=int, default=128, help="trials per GPU")
+    ap.add_argument("--workload", default="epinions", choices=sorted(WORKLOADS),
+                    help="epinions = the metric's configuration (default); ba2m = the 2M-node stress graph (use --trials 8)")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="trials per pipelined chunk of the e2e loop")
     ap.add_argument("--ref-trials", type=int, default=2)
     ap.add_argument("--ref-points", type=int, default=20)
@@ -213,7 +222,7 @@ def main():
     gn.build_library()
     L = _lib.lib()
 
-    A, x_host, orc = build_workload(args.trials, rank * args.trials)
+    A, x_host, orc = build_workload(args.trials, rank * args.trials, args.workload)
     N = A.shape[0]
     T = len(np.arange(0, MAXTIME, DELTAT))
     torch.manual_seed(0)

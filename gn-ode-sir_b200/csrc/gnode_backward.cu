@@ -17,16 +17,17 @@
 // where D(y, gP) is the decoder+softmax backward. Then the encoder backward on a_0.
 //
 // Per reverse step three launches (two grid-wide dependencies: I' before A I', gAI before A^T gAI):
-//   K1 bwd_transform_kernel : S' = sig(S_j W^T+b), I' = sig(I_j W^T+b)          -> Sp, Ip
+//   K1 bwd_transform_kernel : S' = sig(S_j W^T+b), I' = sig(I_j W^T+b)  (tcgen05)  -> Sp, Ip
 //   K2 bwd_row_kernel       : AI = A I' ; a += D(y_j,gP_j) (adjoint mode) ; gAI   -> AI, G, a
 //                             (discrete mode adds D in a separate row pass after K3)
-//   K3 bwd_vjp_kernel       : A^T gAI, gz*, v = gz W into a, per-CTA vW / vb
+//   K3 bwd_vjp_kernel       : A^T gAI, gz*, per-CTA vW / vb (FFMA), v = gz W into a (tcgen05)
 // Parameter-gradient partial sums live in per-CTA slots (no atomics: bitwise reproducible) and are
 // folded by reduce_partials_kernel at the end.
 #include <algorithm>
 
 #include "gnode_common.cuh"
 #include "gnode_tile.cuh"
+#include "gnode_umma.cuh"
 
 namespace gnode {
 
@@ -49,33 +50,46 @@ struct BwdArgs {
 };
 
 // ---------------------------------------------------------------- K1
-constexpr int K1_SM_X = 0, K1_SM_O = 32768, K1_SM_W = 65536, K1_SM_B = K1_SM_W + H * H * 4, K1_SM_TOTAL = K1_SM_B + H * 4;
+// S' and I' of the stored state, recomputed with the forward's tcgen05 4-term tf32 split product (gnode_umma.cuh).
+constexpr int K1_SM_X = 0, K1_SM_O = 32768, K1_SM_WHI = 65536, K1_SM_WLO = K1_SM_WHI + H * H * 4,
+              K1_SM_B = K1_SM_WLO + H * H * 4, K1_SM_BAR = K1_SM_B + H * 4, K1_SM_TOTAL = K1_SM_BAR + 16 + 1024;
 
 __global__ void __launch_bounds__(NTHREADS, 2) bwd_transform_kernel(const BwdArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* Xs = smem + K1_SM_X;
     unsigned char* Os = smem + K1_SM_O;
-    float* Ws = reinterpret_cast<float*>(smem + K1_SM_W);
     float* bs = reinterpret_cast<float*>(smem + K1_SM_B);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + K1_SM_BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + K1_SM_BAR + 8);
     const int tid = threadIdx.x;
     const int M = a.bv.M;
     const size_t plane = (size_t)M * H;
-    for (int i = tid; i < H * H / 4; i += NTHREADS)
-        reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+    umma::prepare_weights(a.p.lin_w, smem + K1_SM_WHI, smem + K1_SM_WLO, tid, NTHREADS);
+    if (tid < 32) umma::tmem_alloc(tslot, umma::TMEM_COLS);
+    if (tid == 0) umma::mbar_init(mbar, 1);
+    umma::fence_before_sync();
     if (tid < H) bs[tid] = a.p.lin_b[tid];
     __syncthreads();
+    umma::fence_after_sync();
+    umma::Ctx cx;
+    cx.tmem = *tslot; cx.bar = mbar; cx.phase = 0;
+    cx.whi = umma::smem_u32(smem + K1_SM_WHI); cx.wlo = umma::smem_u32(smem + K1_SM_WLO);
     for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
         const int64_t tile0 = (int64_t)tile * TILE;
 #pragma unroll 1
         for (int comp = 0; comp < 2; ++comp) {
             load_tile(Xs, a.y + comp * plane, tile0, M, tid);
             __syncthreads();
-            gemm_sigmoid<false>(Xs, Ws, bs, Os, tid);
+            umma::gemm_sigmoid_tc<false>(cx, Xs, Os, bs, tid);      // Xs -> tf32 hi, Os: lo, then the result
             __syncthreads();
             store_tile(comp == 0 ? a.Sp : a.Ip, Os, tile0, M, tid);
             __syncthreads();
         }
     }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- decoder backward for one row
@@ -226,21 +240,38 @@ __global__ void __launch_bounds__(ROW_THREADS) bwd_row_kernel(const BwdArgs a) {
 }
 
 // ---------------------------------------------------------------- K3
-constexpr int K3_SM_GS = 0, K3_SM_GI = 32768, K3_SM_XS = 65536, K3_SM_XI = 98304, K3_SM_W = 131072,
-              K3_SM_TOTAL = K3_SM_W + H * H * 4;
+// Shared memory: gzS | gzI | S_j | I_j tiles (fp32, swizzled) | W^T operand tiles (tf32 hi / lo). The state-VJP
+// v = gz W runs on tcgen05 as the same 4-term tf32 split product as the forward transform: after the weight-gradient
+// phase has consumed the raw tiles, gz is split IN PLACE (gz tile <- hi, the dead state tile <- lo).
+constexpr int K3_SM_GS = 0, K3_SM_GI = 32768, K3_SM_XS = 65536, K3_SM_XI = 98304, K3_SM_WTHI = 131072,
+              K3_SM_WTLO = K3_SM_WTHI + H * H * 4, K3_SM_BAR = K3_SM_WTLO + H * H * 4, K3_SM_TOTAL = K3_SM_BAR + 16 + 1024;
 
 __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* GS = smem + K3_SM_GS;
     unsigned char* GI = smem + K3_SM_GI;
     unsigned char* XS = smem + K3_SM_XS;
     unsigned char* XI = smem + K3_SM_XI;
-    float* Ws = reinterpret_cast<float*>(smem + K3_SM_W);
-    const int tid = threadIdx.x, lane = tid & 31, l = tid & 15, hw = tid >> 4;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + K3_SM_BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + K3_SM_BAR + 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l = tid & 15, hw = tid >> 4;
     const int M = a.bv.M;
     const size_t plane = (size_t)M * H;
-    for (int i = tid; i < H * H / 4; i += NTHREADS)
-        reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(a.p.lin_w)[i];
+    // B operand of v[r][j] = sum_h gz[r][h] W[h][j]: row n = j, K index = h, i.e. W transposed
+    for (int idx = tid; idx < H * CHUNKS; idx += NTHREADS) {
+        const int n = idx >> 4, c4 = idx & 15;
+        const float4 w = make_float4(a.p.lin_w[(4 * c4 + 0) * H + n], a.p.lin_w[(4 * c4 + 1) * H + n],
+                                     a.p.lin_w[(4 * c4 + 2) * H + n], a.p.lin_w[(4 * c4 + 3) * H + n]);
+        float4 hi, lo;
+        umma::tf32_split4(w, hi, lo);
+        sts4(smem + K3_SM_WTHI, umma::swb_off(n, c4), hi);
+        sts4(smem + K3_SM_WTLO, umma::swb_off(n, c4), lo);
+    }
+    umma::fence_proxy_async();
+    if (tid < 32) umma::tmem_alloc(tslot, 128);        // two [128 x 64] fp32 accumulators: vS, vI
+    if (tid == 0) umma::mbar_init(mbar, 2);            // one phase = the commits of both GEMMs
+    umma::fence_before_sync();
 
     // weight-gradient accumulators: thread (h = tid>>3, js = tid&7) owns vW[h][8js..8js+7] (+ vb[h] if js==0)
     const int wh = tid >> 3, wjs = tid & 7;
@@ -249,10 +280,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
     for (int i = 0; i < 8; ++i) gw[i] = 0.f;
     float gb = 0.f;
     __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t wthi = umma::smem_u32(smem + K3_SM_WTHI), wtlo = umma::smem_u32(smem + K3_SM_WTLO);
+    uint32_t phase = 0;
 
     for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
         const int64_t tile0 = (int64_t)tile * TILE;
-        // state tiles for the weight gradient (asynchronous; waited on before the GEMM phase)
+        // state tiles for the weight gradient (asynchronous; waited on before the weight-gradient phase)
         for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
             const int rr = idx >> 4, c4 = idx & 15;
             const int64_t g = tile0 + rr;
@@ -305,31 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
         }
         cp_async_wait_all();
         __syncthreads();
-        // ---- v = gz W into the adjoint: warps 0-7 -> aS, warps 8-15 -> aI (aR: vR = 0)
-        {
-            const int t = tid & 255;
-            const int comp = tid >> 8;
-            float v0[16], v1[16];
-            gemm_gw(comp == 0 ? GS : GI, Ws, t, v0, v1);
-            const int r0 = t & 63, q = t >> 6;
-            float* ap = a.a + comp * plane;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int64_t g = tile0 + r0 + 64 * half;
-                if (g < M) {
-                    float* row = ap + (size_t)g * H + 16 * q;
-#pragma unroll
-                    for (int jj = 0; jj < 16; jj += 4) {
-                        float4 cur = ldg4(row + jj);
-                        const float* v = half == 0 ? v0 : v1;
-                        cur.x = fmaf(a.dt, v[jj + 0], cur.x); cur.y = fmaf(a.dt, v[jj + 1], cur.y);
-                        cur.z = fmaf(a.dt, v[jj + 2], cur.z); cur.w = fmaf(a.dt, v[jj + 3], cur.w);
-                        stg4(row + jj, cur);
-                    }
-                }
-            }
-        }
-        // ---- vW[h][j] += sum_r gzS[r][h] S[r][j] + gzI[r][h] I[r][j] ; vb[h] += sum_r gzS + gzI
+        // ---- vW[h][j] += sum_r gzS[r][h] S[r][j] + gzI[r][h] I[r][j] ; vb[h] += sum_r gzS + gzI   (fp32 FFMA)
 #pragma unroll 4
         for (int r = 0; r < TILE; ++r) {
             const float gs = *reinterpret_cast<const float*>(GS + sw_off(r, wh >> 2) + 4 * (wh & 3));
@@ -343,11 +354,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
             gb += gs + gi;
         }
         __syncthreads();
+        // ---- v = gz W on tcgen05: split gz in place (gz tile <- hi, state tile <- lo), two GEMMs, one mbarrier phase
+        for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
+            const int off = sw_off(idx >> 4, idx & 15);
+            float4 hi, lo;
+            umma::tf32_split4(lds4(GS, off), hi, lo);
+            sts4(GS, off, hi); sts4(XS, off, lo);
+            umma::tf32_split4(lds4(GI, off), hi, lo);
+            sts4(GI, off, hi); sts4(XI, off, lo);
+        }
+        umma::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::issue_split_gemm_to(tmem, mbar, wthi, wtlo, umma::smem_u32(GS), umma::smem_u32(XS));
+            umma::issue_split_gemm_to(tmem + 64, mbar, wthi, wtlo, umma::smem_u32(GI), umma::smem_u32(XI));
+        }
+        umma::mbar_wait(mbar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+        // ---- a += dt * v: warp (q = lane quarter, cq = 16-column block), thread = tile row; aS from vS, aI from vI (vR = 0)
+        {
+            const int q = warp & 3, cq = warp >> 2;
+            const int64_t g = tile0 + q * 32 + lane;
+#pragma unroll
+            for (int comp = 0; comp < 2; ++comp) {
+                float v[16];
+                umma::tmem_ld16(tmem + 64 * comp + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+                if (g < M) {
+                    float* row = a.a + comp * plane + (size_t)g * H + 16 * cq;
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj += 4) {
+                        float4 cur = ldg4(row + jj);
+                        cur.x = fmaf(a.dt, v[jj + 0], cur.x); cur.y = fmaf(a.dt, v[jj + 1], cur.y);
+                        cur.z = fmaf(a.dt, v[jj + 2], cur.z); cur.w = fmaf(a.dt, v[jj + 3], cur.w);
+                        stg4(row + jj, cur);
+                    }
+                }
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
     }
     float* slot = a.part + (size_t)blockIdx.x * LIN_COUNT;
 #pragma unroll
     for (int i = 0; i < 8; ++i) slot[wh * H + 8 * wjs + i] += a.dt * gw[i];
     if (wjs == 0) slot[H * H + wh] += a.dt * gb;
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tmem, 128);
 }
 
 // ---------------------------------------------------------------- K4: encoder backward

@@ -48,3 +48,42 @@ EPINIONS_N = 75879        # node count of SNAP soc-Epinions1
 def epinions_standin(seed=0):
     """BA(N=75,879, m=5): ~379k undirected edges, mean degree ~10 (epinions: ~10.7)."""
     return barabasi_albert_csr(EPINIONS_N, 5, seed)
+
+
+def barabasi_albert_csr_fast(n, m, seed=0, chunk=4096):
+    """Chunked preferential attachment for the multi-million-node stress graphs (BASELINE.json configs[4]):
+    the nodes of one chunk draw their m targets from the endpoint list as it stood at the start of the chunk
+    (degree-proportional up to that lag), so the generator is vectorised and runs in seconds for n = 2e6.
+    Duplicate targets of a node are merged (a few nodes end with fewer than m new edges). Symmetric CSR."""
+    rng = np.random.RandomState(seed)
+    n0 = max(m + 1, min(n, 64))
+    a0 = barabasi_albert_csr(n0, m, seed).tocoo()
+    src = [a0.row[a0.row > a0.col].astype(np.int64)]
+    dst = [a0.col[a0.row > a0.col].astype(np.int64)]
+    endpoints = np.empty(2 * m * n + 2 * len(src[0]), dtype=np.int64)
+    fill = 2 * len(src[0])
+    endpoints[:fill] = np.concatenate((src[0], dst[0]))
+    v = n0
+    while v < n:
+        c = min(chunk, n - v, max(64, v // 4))
+        nodes = np.arange(v, v + c, dtype=np.int64)
+        t = endpoints[rng.randint(0, fill, size=(c, m))]
+        s_ = np.repeat(nodes, m)
+        t_ = t.reshape(-1)
+        src.append(s_); dst.append(t_)
+        endpoints[fill:fill + c * m] = s_
+        endpoints[fill + c * m:fill + 2 * c * m] = t_
+        fill += 2 * c * m
+        v += c
+    src = np.concatenate(src); dst = np.concatenate(dst)
+    rows = np.concatenate((src, dst)); cols = np.concatenate((dst, src))
+    A = scipy.sparse.csr_matrix((np.ones(len(rows), dtype=np.int8), (rows, cols)), shape=(n, n))
+    A.sum_duplicates()
+    A.data[:] = 1
+    A.sort_indices()
+    return A
+
+
+def ba_stress(seed=0):
+    """BA(N=2,000,000, m=10): ~20M undirected edges, mean degree ~20 (BASELINE.json configs[4])."""
+    return barabasi_albert_csr_fast(2_000_000, 10, seed)
