@@ -152,7 +152,7 @@ __device__ __forceinline__ void decoder_backward_row(const float4 (&c)[3], const
 }
 
 // ---------------------------------------------------------------- K2
-__global__ void __launch_bounds__(ROW_THREADS) bwd_row_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a) {
     __shared__ float W3s[4 * H];
     __shared__ float small[12];
     __shared__ float red[ROW_THREADS / 16][16][17];   // [half-warp][lane][16 w3 values (+pad)]
@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(ROW_THREADS) bwd_row_kernel(const BwdArgs a) {
             int row0 = 0, e0 = 0, deg = 0;
             const int32_t* ci = nullptr;
             if (valid) {
-                const GnInstance I = a.bv.inst[find_instance(a.bv, g)];
+                int inst = a.bv.tile_inst[g / TILE];                 // owner of the tile's first row, then walk forward
+                while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                const GnInstance I = a.bv.inst[inst];
                 row0 = I.row0; ci = I.colidx;
                 const int n = (int)(g - row0);
                 e0 = I.rowptr[n];
@@ -273,12 +275,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
     if (tid == 0) umma::mbar_init(mbar, 2);            // one phase = the commits of both GEMMs
     umma::fence_before_sync();
 
-    // weight-gradient accumulators: thread (h = tid>>3, js = tid&7) owns vW[h][8js..8js+7] (+ vb[h] if js==0)
-    const int wh = tid >> 3, wjs = tid & 7;
-    float gw[8];
+    // weight-gradient accumulators, register-blocked 8 (h) x 4 (j) so that one row costs 3 shared-memory loads per 32
+    // FMAs (the previous 1 x 8 blocking was bound by the shared-memory queue: mio_throttle 36 %). Thread = (part:
+    // gzS (x) S or gzI (x) I, row group of 64 rows, h block of 8, 16-byte column chunk); the four partial sums per
+    // output element are folded through shared memory at the end of the kernel, in a fixed order.
+    const int wpart = tid >> 8, wrg = (tid >> 7) & 1, whb = (tid >> 4) & 7, wjq = tid & 15;
+    float gw[32], gb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gw[i] = 0.f;
-    float gb = 0.f;
+    for (int i = 0; i < 32; ++i) gw[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gb[i] = 0.f;
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = *tslot;
@@ -341,17 +347,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
         cp_async_wait_all();
         __syncthreads();
         // ---- vW[h][j] += sum_r gzS[r][h] S[r][j] + gzI[r][h] I[r][j] ; vb[h] += sum_r gzS + gzI   (fp32 FFMA)
-#pragma unroll 4
-        for (int r = 0; r < TILE; ++r) {
-            const float gs = *reinterpret_cast<const float*>(GS + sw_off(r, wh >> 2) + 4 * (wh & 3));
-            const float gi = *reinterpret_cast<const float*>(GI + sw_off(r, wh >> 2) + 4 * (wh & 3));
-            const float4 s0 = lds4(XS, sw_off(r, 2 * wjs)), s1 = lds4(XS, sw_off(r, 2 * wjs + 1));
-            const float4 i0 = lds4(XI, sw_off(r, 2 * wjs)), i1 = lds4(XI, sw_off(r, 2 * wjs + 1));
-            gw[0] = fmaf(gs, s0.x, gw[0]); gw[1] = fmaf(gs, s0.y, gw[1]); gw[2] = fmaf(gs, s0.z, gw[2]); gw[3] = fmaf(gs, s0.w, gw[3]);
-            gw[4] = fmaf(gs, s1.x, gw[4]); gw[5] = fmaf(gs, s1.y, gw[5]); gw[6] = fmaf(gs, s1.z, gw[6]); gw[7] = fmaf(gs, s1.w, gw[7]);
-            gw[0] = fmaf(gi, i0.x, gw[0]); gw[1] = fmaf(gi, i0.y, gw[1]); gw[2] = fmaf(gi, i0.z, gw[2]); gw[3] = fmaf(gi, i0.w, gw[3]);
-            gw[4] = fmaf(gi, i1.x, gw[4]); gw[5] = fmaf(gi, i1.y, gw[5]); gw[6] = fmaf(gi, i1.z, gw[6]); gw[7] = fmaf(gi, i1.w, gw[7]);
-            gb += gs + gi;
+        {
+            const unsigned char* Gt = wpart == 0 ? GS : GI;
+            const unsigned char* Xt = wpart == 0 ? XS : XI;
+#pragma unroll 2
+            for (int r = 64 * wrg; r < 64 * wrg + 64; ++r) {
+                const float4 g0 = lds4(Gt, sw_off(r, 2 * whb)), g1 = lds4(Gt, sw_off(r, 2 * whb + 1));
+                const float4 xv = lds4(Xt, sw_off(r, wjq));
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int hh = 0; hh < 8; ++hh) {
+                    gw[4 * hh + 0] = fmaf(g[hh], xv.x, gw[4 * hh + 0]); gw[4 * hh + 1] = fmaf(g[hh], xv.y, gw[4 * hh + 1]);
+                    gw[4 * hh + 2] = fmaf(g[hh], xv.z, gw[4 * hh + 2]); gw[4 * hh + 3] = fmaf(g[hh], xv.w, gw[4 * hh + 3]);
+                }
+                if (wjq == 0) {
+#pragma unroll
+                    for (int hh = 0; hh < 8; ++hh) gb[hh] += g[hh];
+                }
+            }
         }
         __syncthreads();
         // ---- v = gz W on tcgen05: split gz in place (gz tile <- hi, state tile <- lo), two GEMMs, one mbarrier phase
@@ -395,10 +408,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
         umma::fence_before_sync();
         __syncthreads();
     }
-    float* slot = a.part + (size_t)blockIdx.x * LIN_COUNT;
+    // fold the four partial sums (part x row group) of every output element: red[4][64][64] over the gz tiles,
+    // red_b[4][64] over the S tile (the tile loop has ended with a block barrier)
+    {
+        float* red = reinterpret_cast<float*>(GS);
+        float* red_b = reinterpret_cast<float*>(XS);
+        const int pidx = tid >> 7;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) slot[wh * H + 8 * wjs + i] += a.dt * gw[i];
-    if (wjs == 0) slot[H * H + wh] += a.dt * gb;
+        for (int hh = 0; hh < 8; ++hh)
+            *reinterpret_cast<float4*>(red + ((size_t)pidx * H + 8 * whb + hh) * H + 4 * wjq) =
+                make_float4(gw[4 * hh + 0], gw[4 * hh + 1], gw[4 * hh + 2], gw[4 * hh + 3]);
+        if (wjq == 0) {
+#pragma unroll
+            for (int hh = 0; hh < 8; ++hh) red_b[pidx * H + 8 * whb + hh] = gb[hh];
+        }
+        __syncthreads();
+        float* slot = a.part + (size_t)blockIdx.x * LIN_COUNT;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = tid * 8 + i;                      // output element (h, j) = (o / 64, o % 64)
+            const float sum = ((red[o] + red[H * H + o]) + red[2 * H * H + o]) + red[3 * H * H + o];
+            slot[o] += a.dt * sum;
+        }
+        if (tid < H) slot[H * H + tid] += a.dt * (((red_b[tid] + red_b[H + tid]) + red_b[2 * H + tid]) + red_b[3 * H + tid]);
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(tmem, 128);
