@@ -16,11 +16,12 @@
 //   a = D(y_{T-1}, gP_{T-1});  for j = T-2 .. 0:  (v, v_theta) = VJP(y_j; a);  a += D(y_j, gP_j) + dt_j v
 // where D(y, gP) is the decoder+softmax backward. Then the encoder backward on a_0.
 //
-// Per reverse step three launches (two grid-wide dependencies: I' before A I', gAI before A^T gAI):
+// Per reverse step four launches (two grid-wide dependencies: I' before A I', gAI before A^T gAI):
 //   K1 bwd_transform_kernel : S' = sig(S_j W^T+b), I' = sig(I_j W^T+b)  (tcgen05)  -> Sp, Ip
 //   K2 bwd_row_kernel       : AI = A I' ; a += D(y_j,gP_j) (adjoint mode) ; gAI   -> AI, G, a
 //                             (discrete mode adds D in a separate row pass after K3)
-//   K3 bwd_vjp_kernel       : A^T gAI, gz*, per-CTA vW / vb (FFMA), v = gz W into a (tcgen05)
+//   K3a bwd_gz_kernel      : A^T gAI, gz* (in place over Sp / AI)
+//   K3 bwd_vjp_kernel       : per-CTA vW / vb (FFMA), v = gz W into a (tcgen05)
 // Parameter-gradient partial sums live in per-CTA slots (no atomics: bitwise reproducible) and are
 // folded by reduce_partials_kernel at the end.
 #include <algorithm>
@@ -241,6 +242,56 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a
     }
 }
 
+// ---------------------------------------------------------------- K3a
+// Row kernel (half-warp per row, grid-stride): A^T gAI, then the cotangents wrt the pre-activations
+//   gzI = (A^T gAI + gamma (aR - aI)) I'(1-I')      gzS = beta (aI - aS) AI S'(1-S')
+// written IN PLACE over the row's own S' (Sp <- gzS) and AI (AI <- gzI): both are read only by this row's threads.
+// Separate from the tile kernel so that this latency-bound gather runs at row-kernel occupancy.
+__global__ void __launch_bounds__(ROW_THREADS, 3) bwd_gz_kernel(const BwdArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, l = tid & 15, hw = tid >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    const int hw_per_grid = gridDim.x * (ROW_THREADS / 16);
+    const int64_t n_iter = (M + hw_per_grid - 1) / hw_per_grid;        // warp-uniform trip count
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t g = it * hw_per_grid + (int64_t)blockIdx.x * (ROW_THREADS / 16) + hw;
+        const bool valid = g < M;
+        const size_t off = (size_t)(valid ? g : 0) * H + 4 * l;
+        int row0 = 0, e0 = 0, deg = 0;
+        const int32_t* ci = nullptr;
+        float be = 0.f, ga = 0.f;
+        float4 aS, aI, aR, sp, ip, ai;
+        if (valid) {
+            aS = ldg4(a.a + off); aI = ldg4(a.a + plane + off); aR = ldg4(a.a + 2 * plane + off);
+            sp = ldg4(a.Sp + off); ip = ldg4_stream(a.Ip + off); ai = ldg4(a.AI + off);
+            int inst = a.bv.tile_inst[g / TILE];
+            while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+            const GnInstance I = a.bv.inst[inst];
+            row0 = I.row0; ci = I.colidx_t;
+            const int n = (int)(g - row0);
+            e0 = I.rowptr_t[n];
+            deg = I.rowptr_t[n + 1] - e0;
+            be = a.x[(size_t)g * a.ldx + 3];
+            ga = a.x[(size_t)g * a.ldx + 4];
+        }
+        const float4 gsum = gather_row(a.G, ci, e0, deg, row0, l, lane);
+        if (valid) {
+            float4 gzs, gzi;
+#define GN_GZ(c)                                                               \
+    {                                                                          \
+        const float q = aI.c - aS.c;                                           \
+        const float gip = gsum.c + ga * (aR.c - aI.c);                         \
+        gzi.c = gip * ip.c * (1.0f - ip.c);                                    \
+        gzs.c = be * q * ai.c * sp.c * (1.0f - sp.c);                          \
+    }
+            GN_GZ(x) GN_GZ(y) GN_GZ(z) GN_GZ(w)
+#undef GN_GZ
+            stg4(a.Sp + off, gzs);
+            stg4(a.AI + off, gzi);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- K3
 // Shared memory: gzS | gzI | S_j | I_j tiles (fp32, swizzled) | W^T operand tiles (tf32 hi / lo). The state-VJP
 // v = gz W runs on tcgen05 as the same 4-term tf32 split product as the forward transform: after the weight-gradient
@@ -257,7 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
     unsigned char* XI = smem + K3_SM_XI;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + K3_SM_BAR);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + K3_SM_BAR + 8);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l = tid & 15, hw = tid >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = a.bv.M;
     const size_t plane = (size_t)M * H;
     // B operand of v[r][j] = sum_h gz[r][h] W[h][j]: row n = j, K index = h, i.e. W transposed
@@ -293,56 +344,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
 
     for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
         const int64_t tile0 = (int64_t)tile * TILE;
-        // state tiles for the weight gradient (asynchronous; waited on before the weight-gradient phase)
+        // gz tiles (written by bwd_gz_kernel over Sp / AI) and state tiles -> shared memory
         for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
             const int rr = idx >> 4, c4 = idx & 15;
             const int64_t g = tile0 + rr;
+            const int so = sw_off(rr, c4);
             if (g < M) {
-                cp_async16(XS + sw_off(rr, c4), a.y + (size_t)g * H + 4 * c4);
-                cp_async16(XI + sw_off(rr, c4), a.y + plane + (size_t)g * H + 4 * c4);
+                const size_t go = (size_t)g * H + 4 * c4;
+                cp_async16(GS + so, a.Sp + go);
+                cp_async16(GI + so, a.AI + go);
+                cp_async16(XS + so, a.y + go);
+                cp_async16(XI + so, a.y + plane + go);
             } else {
-                sts4(XS, sw_off(rr, c4), make_float4(0.f, 0.f, 0.f, 0.f));
-                sts4(XI, sw_off(rr, c4), make_float4(0.f, 0.f, 0.f, 0.f));
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                sts4(GS, so, z); sts4(GI, so, z); sts4(XS, so, z); sts4(XI, so, z);
             }
-        }
-        // ---- row phase: A^T gAI, then the cotangents wrt the pre-activations
-        int inst = a.bv.tile_inst[tile];
-#pragma unroll 1
-        for (int it = 0; it < TILE / 32; ++it) {
-            const int rr = hw + 32 * it;
-            const int64_t g = tile0 + rr;
-            const bool valid = g < M;
-            int row0 = 0, e0 = 0, deg = 0;
-            const int32_t* ci = nullptr;
-            float be = 0.f, ga = 0.f;
-            if (valid) {
-                while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
-                const GnInstance I = a.bv.inst[inst];
-                row0 = I.row0; ci = I.colidx_t;
-                const int n = (int)(g - row0);
-                e0 = I.rowptr_t[n];
-                deg = I.rowptr_t[n + 1] - e0;
-                be = a.x[(size_t)g * a.ldx + 3];
-                ga = a.x[(size_t)g * a.ldx + 4];
-            }
-            const float4 gsum = gather_row(a.G, ci, e0, deg, row0, l, lane);
-            float4 gzs = make_float4(0.f, 0.f, 0.f, 0.f), gzi = gzs;
-            if (valid) {
-                const size_t off = (size_t)g * H + 4 * l;
-                const float4 aS = ldg4(a.a + off), aI = ldg4(a.a + plane + off), aR = ldg4(a.a + 2 * plane + off);
-                const float4 sp = ldg4_stream(a.Sp + off), ip = ldg4_stream(a.Ip + off), ai = ldg4_stream(a.AI + off);
-#define GN_GZ(c)                                                               \
-    {                                                                          \
-        const float q = aI.c - aS.c;                                           \
-        const float gip = gsum.c + ga * (aR.c - aI.c);                         \
-        gzi.c = gip * ip.c * (1.0f - ip.c);                                    \
-        gzs.c = be * q * ai.c * sp.c * (1.0f - sp.c);                          \
-    }
-                GN_GZ(x) GN_GZ(y) GN_GZ(z) GN_GZ(w)
-#undef GN_GZ
-            }
-            sts4(GS, sw_off(rr, l), gzs);
-            sts4(GI, sw_off(rr, l), gzi);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -567,6 +583,9 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
         GN_LAUNCH_CHECK();
         a.part = pdec;
         bwd_row_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+        GN_LAUNCH_CHECK();
+        a.part = nullptr;
+        bwd_gz_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
         a.part = plin;
         bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
