@@ -1,0 +1,85 @@
+"""Edge cases of the rollout path the golden fixtures do not reach: hub rows longer than the staged CSR slice,
+isolated nodes, self-loops, directed adjacency, and the full-size bench graph (kernel structures against each other)."""
+import numpy as np
+import pytest
+import scipy.sparse
+import torch
+
+from oracle import gnode_oracle as orc
+from test_parity_gpu import DEV, dev_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gn():
+    import gn_ode_sir_b200 as g
+    g.build_library()
+    return g
+
+
+def _rollout(gn, A, B, seed, maxTime=20, deltaT=0.5):
+    N = A.shape[0]
+    params = orc.default_params(64, seed=seed)
+    x = torch.cat([orc.synthetic_trial(N, 64, 300 + b) for b in range(B)])
+    t = orc.time_grid(maxTime, deltaT)
+    want = orc.forward(x, params, orc.batch_coo([A], [0] * B), t)
+    graph = gn.DeviceGraph(A)
+    with torch.no_grad():
+        got = gn.rollout.rollout(x.to(DEV), gn.DeviceBatch([graph] * B), gn.rollout.dt_array(t), dev_params(params)).cpu()
+    return got, want, graph
+
+
+def test_star_hub_isolated_nodes_and_self_loops(gn):
+    """One hub with 4000 neighbours (longer than the 1536-entry staged slice and than one 12-row gather round),
+    200 isolated nodes (degree 0) and a few self-loops (counted once, like the reference's scatter_add_)."""
+    n = 4300
+    rows = np.concatenate((np.zeros(4000, dtype=np.int64), np.arange(1, 4001), [7, 9, 4100]))
+    cols = np.concatenate((np.arange(1, 4001), np.zeros(4000, dtype=np.int64), [7, 9, 4100]))
+    A = scipy.sparse.csr_matrix((np.ones(len(rows), dtype=np.int64), (rows, cols)), shape=(n, n))
+    A.sum_duplicates(); A.data[:] = 1; A.sort_indices()
+    got, want, graph = _rollout(gn, A, B=3, seed=21, maxTime=6, deltaT=0.5)
+    assert graph.max_degree == 4000
+    assert torch.isfinite(got).all()
+    # the hub's state saturates; compare the probabilities of every node
+    assert (got - want).abs().max().item() < 1e-5
+
+
+def test_directed_graph_rollout(gn):
+    """Non-symmetric adjacency: the forward aggregates over the stored (row, col) entries, not their transpose."""
+    rng = np.random.RandomState(4)
+    A = scipy.sparse.random(700, 700, density=0.01, random_state=rng, format="csr")
+    A.data[:] = 1
+    A = A.astype(np.int64)
+    got, want, graph = _rollout(gn, A, B=2, seed=22, maxTime=10, deltaT=0.5)
+    assert not graph.symmetric
+    assert (got - want).abs().max().item() < 1e-5
+
+
+def test_bench_graph_kernel_structures_agree(gn):
+    """Full-size epinions stand-in (BA N=75,879: hub tiles, slice overflow, partial last tile), 3 trials: the pipelined
+    tensor-core kernel (2 x 128 and 4 x 64 rows) against the generic fp32 FFMA kernel that the goldens validate."""
+    from gn_ode_sir_b200 import _lib, synth
+    L = _lib.lib()
+    A = synth.epinions_standin(0)
+    N, B = A.shape[0], 3
+    params = dev_params(orc.default_params(64, seed=0))
+    x = torch.cat([orc.synthetic_trial(N, 64, 500 + b) for b in range(B)]).to(DEV)
+    graph = gn.DeviceGraph(A)
+    batch = gn.DeviceBatch([graph] * B)
+    dt = gn.rollout.dt_array(orc.time_grid(20, 0.5))
+    prev_k, prev_v = L.gnode_get_step_kernel(), L.gnode_get_variant()
+    out = {}
+    try:
+        for name, kern, var in (("dual", 3, 3), ("quad", 4, 3), ("ffma", 0, 0)):
+            _lib.check(L.gnode_set_step_kernel(kern), "set_step_kernel")
+            _lib.check(L.gnode_set_variant(var), "set_variant")
+            with torch.no_grad():
+                out[name] = gn.rollout.rollout(x, batch, dt, params).cpu()
+    finally:
+        L.gnode_set_step_kernel(prev_k); L.gnode_set_variant(prev_v)
+    for name in ("dual", "quad"):
+        err = (out[name] - out["ffma"]).abs().max().item()
+        print("%s vs fp32 FFMA kernel on the bench graph: %.3e" % (name, err))
+        assert err < 5e-6, (name, err)
+    assert (out["dual"].sum(-1) - 1).abs().max().item() < 1e-6
