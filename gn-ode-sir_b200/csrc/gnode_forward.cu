@@ -12,6 +12,7 @@
 // so one launch per step reads S,I,R,I' and writes S,I,R,I',probs exactly once; the
 // grid-wide dependency (all of I'_k before any aggregation) is the launch boundary.
 // The reference's R' = sigmoid(linear(R)) is never used (:66 vs :75-77) and is skipped.
+#include <cuda.h>          // CUtensorMap (type and enums only: the encoder is resolved through the runtime, no libcuda link)
 #include <algorithm>
 #include <cstdlib>
 
@@ -44,6 +45,8 @@ struct StepArgs {
     int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
     int* counter;         // dynamic tile scheduler (one zeroed int per launch) or null = static striding
     gnode_params_t p;
+    int use_tma;          // dual kernel: I'_{k+1} tiles leave shared memory through TMA stores described by tm_ip_out
+    alignas(64) CUtensorMap tm_ip_out;   // [M rows][64] fp32 over ip_out, box 32 x 128, SWIZZLE_128B
 };
 
 // shared-memory carve-up (bytes from a 1024-B aligned base; operand tiles need 1024-B alignment)
@@ -303,6 +306,12 @@ __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// TMA tensor store of one box (shared memory -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(umma::smem_u32(smem_src)), "l"(pol) : "memory");
 }
 
 // decoder + softmax with a 20-shuffle butterfly: after 4 halving exchange stages lane l of the
@@ -788,7 +797,7 @@ struct PipeCfg {
 };
 
 template <bool FAST, int NP>
-__global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_constant__ StepArgs a) {
     using C = PipeCfg<NP>;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
     extern __shared__ unsigned char smem_raw[];
@@ -1112,10 +1121,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const StepArgs 
             }
         }
         umma::fence_before_sync();
+        umma::fence_proxy_async();                       // the staged tile is read by the TMA (async proxy)
         HSYNC();                                                                // S4 (the next tile's metadata is published)
         GN_TICK(5)
-        // ---- P5: coalesced store of I'_{k+1}
-        {
+        // ---- P5: I'_{k+1} tile -> HBM. TR = 128: two TMA tensor stores (one per 128-byte K-block of the swizzled staging
+        //      tile; rows past M are clipped by the tensor bounds) issued by one thread, no LSU traffic; the tile may be
+        //      overwritten once the bulk group has finished READING shared memory. Otherwise: coalesced LSU stores.
+        if (NP == 2 && a.use_tma) {
+            if (t == 0 && !(a.dbg & 16384)) {
+                tma_store_2d(&a.tm_ip_out, Ls, 0, tile0, pol_stream);
+                tma_store_2d(&a.tm_ip_out, Ls + C::KBLK, 32, tile0, pol_stream);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else {
             float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1594,6 +1613,36 @@ static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t str
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows][64] fp32 row-major, box = 32 floats (one 128-byte swizzle span) x 128 rows
+static bool encode_rows_map(CUtensorMap* tm, float* base, size_t rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || rows == 0) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)H * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace gnode
 
 using namespace gnode;
@@ -1680,12 +1729,16 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     }
     a.counter = (a.dbg & 64) ? nullptr : counters;
     const bool dual = use_dual();
+    a.use_tma = 0;
+    CUtensorMap tm_ip[2];
+    const bool have_tma = dual && !(a.dbg & 32768) && encode_rows_map(&tm_ip[0], ip[0], M) && encode_rows_map(&tm_ip[1], ip[1], M);
     a.hid_i = dual ? hid_i : nullptr;
     int rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
     for (int k = 0; k + 1 < T; ++k) {
         a.y_in = state(k); a.y_out = state(k + 1);
         a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
+        if (have_tma) { a.use_tma = 1; a.tm_ip_out = tm_ip[(k + 1) & 1]; }
         // dual kernel: step k decodes its input state k (k = 0 is the encoder's); the others decode their output
         a.probs = dual ? (k > 0 ? probs + (size_t)k * M * 3 : nullptr) : probs + (size_t)(k + 1) * M * 3;
         a.dt = dt_host[k];
@@ -1712,7 +1765,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr; a.use_tma = 0;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;
