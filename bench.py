@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--trials", type=int, default=128, help="trials per GPU")
     ap.add_argument("--workload", default="epinions", choices=sorted(WORKLOADS),
                     help="epinions = the metric's configuration (default); ba2m = the 2M-node stress graph (use --trials 8)")
-    ap.add_argument("--e2e-chunk", type=int, default=16, help="trials per pipelined chunk of the e2e loop")
+    ap.add_argument("--e2e-chunk", type=int, default=32, help="trials per pipelined chunk of the e2e loop")
     ap.add_argument("--ref-trials", type=int, default=2)
     ap.add_argument("--ref-points", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,7 +281,8 @@ def main():
     # ---------------- end-to-end through the public API with host buffers
     # The caller's loop: pinned host x -> device, ODEBlock.forward, probabilities -> pinned host. The trials
     # are fed in chunks over three streams so that the PCIe copies of chunk c-1 / c+1 overlap the rollout
-    # of chunk c (plain PyTorch stream code around the drop-in module; every byte is copied every step).
+    # of chunk c (plain PyTorch stream code around the drop-in module; every byte is copied every step; the
+    # K timed steps form one continuous stream of chunks, timed from the first H2D to the last D2H).
     bc = max(1, min(args.e2e_chunk, args.trials))
     n_chunks = (args.trials + bc - 1) // bc
     x_pin = x_host.pin_memory()
@@ -294,15 +295,18 @@ def main():
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_cmp = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
+    def e2e_steps(n_steps):
+        """n_steps passes over this rank's trials as ONE continuous stream of chunks (a long job does not drain the
+        pipeline between batches): H2D of chunk i+1 and D2H of chunk i-1 overlap the rollout of chunk i."""
         main = torch.cuda.current_stream()
         for st in (s_in, s_cmp, s_out):
             st.wait_stream(main)
-        for c in range(n_chunks):
-            b0, b1, buf = c * bc, min(args.trials, (c + 1) * bc), c % 2
+        for i in range(n_steps * n_chunks):
+            c = i % n_chunks
+            b0, b1, buf = c * bc, min(args.trials, (c + 1) * bc), i % 2
             with torch.cuda.stream(s_in):
-                if c >= 2:
-                    s_in.wait_event(ev_free[buf])                       # rollout of chunk c-2 has consumed xd[buf]
+                if i >= 2:
+                    s_in.wait_event(ev_free[buf])                       # rollout of chunk i-2 has consumed xd[buf]
                 xd[buf][:b1 - b0].copy_(x_pin[b0:b1], non_blocking=True)
                 ev_in[buf].record(s_in)
             with torch.cuda.stream(s_cmp):
@@ -319,13 +323,11 @@ def main():
             main.wait_stream(st)
 
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
+        e2e_steps(max(1, min(args.warmup, 2)))
         barrier()
         ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev2[0].record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_steps(args.steps)
         ev2[1].record()
         barrier()
         e2e_ms = max_over_ranks(ev2[0].elapsed_time(ev2[1])) / args.steps
