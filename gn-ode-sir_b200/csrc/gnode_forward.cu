@@ -835,7 +835,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
 
     // one thread: draw the next sequence number and resolve its metadata (3 dependent loads of small tables)
     auto fetch_meta = [&](int k) {
-        int seq = a.counter ? atomicAdd(a.counter, 1) : NP * (int)blockIdx.x + half + NP * k * (int)gridDim.x;
+        // first tile: static, CTA-major (a batch with fewer tiles than pipelines is spread one tile per SM, and the
+        // launch starts without a burst of atomics); later tiles: dynamic ticket
+        const int first = (int)blockIdx.x + half * (int)gridDim.x;
+        int seq = k == 0 ? first : (a.counter ? NP * (int)gridDim.x + atomicAdd(a.counter, 1) : first + NP * k * (int)gridDim.x);
         if ((a.dbg & 2048) && half != 0) seq = n_tiles;               // timing experiment: one pipeline per SM
         DTileMeta m;
         m.seq = seq; m.rowptr = nullptr; m.colidx = nullptr;
@@ -1575,7 +1578,7 @@ static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_
         configured[b->device & 63] = true;
     }
     const int units = (NP == 2 ? 1 : 2) * b->n_tiles;
-    const int grid = std::min((units + NP - 1) / NP, b->sm_count);
+    const int grid = std::min(units, b->sm_count);          // small batches: one tile per SM before a second pipeline is used
     step_dual_kernel<FAST, NP><<<grid, D_THREADS, PipeCfg<NP>::TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;

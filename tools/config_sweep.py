@@ -1,0 +1,69 @@
+"""Rollout throughput over the BASELINE.json / SURVEY 8d configurations (inference, inputs resident in HBM, CUDA events):
+graph sizes of the reference's datasets as BA stand-ins (the pickles do not travel to the GPU box), trial counts and
+maxTime sweep on the epinions stand-in, and a heavier-tailed variant (hub degree ~3k like soc-Epinions1)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, scipy.sparse, torch
+import gn_ode_sir_b200 as gn
+from gn_ode_sir_b200 import synth
+from oracle import gnode_oracle as orc
+
+dev = torch.device("cuda:0")
+
+
+def heavy_tail(A, n_hubs=8, hub_deg=3000, seed=1):
+    """adds n_hubs hubs of degree ~hub_deg to a BA graph (max degree ~3k, like soc-Epinions1)"""
+    rng = np.random.RandomState(seed)
+    N = A.shape[0]
+    rows, cols = [], []
+    for h in range(n_hubs):
+        nb = rng.choice(N, hub_deg, replace=False)
+        nb = nb[nb != h]
+        rows += [np.full(len(nb), h), nb]; cols += [nb, np.full(len(nb), h)]
+    B = scipy.sparse.csr_matrix((np.ones(sum(len(r) for r in rows), dtype=np.int8), (np.concatenate(rows), np.concatenate(cols))), shape=A.shape)
+    C = (A + B).tocsr(); C.sum_duplicates(); C.data[:] = 1; C.sort_indices()
+    return C
+
+
+def run(name, A, B, maxTime, reps=3):
+    N = A.shape[0]
+    torch.manual_seed(0)
+    of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, dev)
+    blk = gn.ode_sim.ODEBlock(maxTime, 0.5, N, [0, 1], 64, of, dev).to(dev).eval()
+    x = torch.zeros(B, N, 67)
+    for b in range(B):
+        rng = np.random.RandomState(1000 + b)
+        s = rng.choice(N, 2, replace=False)
+        x[b, :, 0] = 1.0; x[b, s, 0] = 0.0; x[b, s, 1] = 1.0
+        x[b, :, 3], x[b, :, 4] = rng.uniform(0.1, 0.5), rng.uniform(0.1, 0.5)
+    x = x.to(dev)
+    T = len(np.arange(0, maxTime, 0.5))
+    with torch.no_grad():
+        for _ in range(2):
+            blk(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            blk(x)
+        e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ns = B * N * (T - 1) / (ms * 1e-3)
+    d = np.diff(A.indptr)
+    print("%-34s N=%-8d maxdeg=%-6d trials=%-5d T=%-4d %9.3f ms  %.3e node-steps/s  (%.1f %% of 3.18e9)" % (
+        name, N, d.max(), B, T, ms, ns, 100 * ns / 3.1826e9), flush=True)
+    del blk, of, x
+    torch.cuda.empty_cache()
+
+
+ep = synth.epinions_standin(0)
+run("karate-size BA(34,2)", synth.barabasi_albert_csr(34, 2, 0), 1, 20)
+for B in (8, 64, 512):
+    run("fb-social-size BA(1893,7)", synth.barabasi_albert_csr(1893, 7, 0), B, 20)
+run("wiki-vote-size BA(7066,14)", synth.barabasi_albert_csr(7066, 14, 0), 64, 20)
+run("enron-size BA(33696,5)", synth.barabasi_albert_csr(33696, 5, 0), 128, 20)
+for B in (16, 64, 128):
+    run("epinions stand-in BA(75879,5)", ep, B, 20)
+for mt in (10, 40, 80):
+    run("epinions stand-in, maxTime sweep", ep, 128, mt)
+run("epinions stand-in + 8 hubs deg 3k", heavy_tail(ep), 128, 20)
