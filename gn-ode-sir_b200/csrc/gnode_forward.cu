@@ -837,7 +837,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     auto fetch_meta = [&](int k) {
         // first tile: static, CTA-major (a batch with fewer tiles than pipelines is spread one tile per SM, and the
         // launch starts without a burst of atomics); later tiles: dynamic ticket
-        const int first = (int)blockIdx.x + half * (int)gridDim.x;
+        const int first = (a.dbg & 524288) ? NP * (int)blockIdx.x + half          // A/B: adjacent first tiles per CTA
+                                           : (int)blockIdx.x + half * (int)gridDim.x;
         int seq = k == 0 ? first : (a.counter ? NP * (int)gridDim.x + atomicAdd(a.counter, 1) : first + NP * k * (int)gridDim.x);
         if ((a.dbg & 2048) && half != 0) seq = n_tiles;               // timing experiment: one pipeline per SM
         DTileMeta m;
