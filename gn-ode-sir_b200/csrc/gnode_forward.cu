@@ -12,6 +12,7 @@
 // so one launch per step reads S,I,R,I' and writes S,I,R,I',probs exactly once; the
 // grid-wide dependency (all of I'_k before any aggregation) is the launch boundary.
 // The reference's R' = sigmoid(linear(R)) is never used (:66 vs :75-77) and is skipped.
+#include <cooperative_groups.h>
 #include <cuda.h>          // CUtensorMap (type and enums only: the encoder is resolved through the runtime, no libcuda link)
 #include <algorithm>
 #include <cstdlib>
@@ -46,7 +47,18 @@ struct StepArgs {
     int* counter;         // dynamic tile scheduler (one zeroed int per launch) or null = static striding
     gnode_params_t p;
     int use_tma;          // dual kernel: I'_{k+1} tiles leave shared memory through TMA stores described by tm_ip_out
+    // persistent rollout (dual kernel, cooperative launch): the kernel runs the Euler steps k0 .. k1-1 itself, with a
+    // grid barrier between steps; per-step pointers are derived from the bases below (n_steps == 0: one step from the
+    // fields above, ordinary launch)
+    int k0, n_steps;
+    float* traj;          // [T][3][M][H] or null (then the two ping-pong buffers st[])
+    float* st[2];
+    float* ipb[2];        // I' ping-pong
+    float* probs_base;    // [T][M][3]
+    const float* dt_dev;  // [T-1] device copy of the step sizes
+    int* counters;        // one zeroed int per step (dynamic tile tickets)
     alignas(64) CUtensorMap tm_ip_out;   // [M rows][64] fp32 over ip_out, box 32 x 128, SWIZZLE_128B
+    alignas(64) CUtensorMap tm_ipb[2];   // the same over ipb[0] / ipb[1] (persistent rollout)
 };
 
 // shared-memory carve-up (bytes from a 1024-B aligned base; operand tiles need 1024-B alignment)
@@ -686,7 +698,7 @@ constexpr int D_W3 = D_B + H * 4;                         // linear3.weight [4][
 constexpr int D_SMALL = D_W3 + 4 * H * 4;                 // b3[4], w2[4], b2
 constexpr int D_TSLOT = D_SMALL + 64;                     // TMEM base slot
 constexpr int D_SHARED = 43008;                           // shared part, rounded up to 1 KB (operand tiles need 1024-B alignment)
-static_assert(D_TSLOT + 16 <= D_SHARED, "shared part overflows");
+static_assert(D_TSLOT + 16 + 64 <= D_SHARED, "shared part overflows (TMEM slot + DStep)");
 // up to 4*NB neighbour rows of one row, all loads issued before the first add (one memory round trip)
 template <int NB>
 __device__ __forceinline__ void gather_block(float4& acc, const float* __restrict__ lane_base, const int* cp, int j0, int deg, uint64_t pol) {
@@ -796,7 +808,17 @@ struct PipeCfg {
     static __device__ __forceinline__ int sw(int r, int c4) { return (c4 >> 3) * KBLK + (r << 7) + (((c4 & 7) ^ (r & 7)) << 4); }
 };
 
-template <bool FAST, int NP>
+// Operands of the Euler step in progress (shared memory, written by one thread per step): keeping them out of
+// registers matters at the 64-register budget of the 1024-thread CTA.
+struct DStep {
+    const float* y_in; float* y_out;
+    const float* ip_in; float* ip_out;
+    float* probs; int* counter;
+    const CUtensorMap* tm;
+    float dt;
+};
+
+template <bool FAST, int NP, bool PERSIST>
 __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_constant__ StepArgs a) {
     using C = PipeCfg<NP>;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
@@ -833,13 +855,18 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     const uint64_t pol_keep = (a.dbg & 256) ? l2_policy_evict_normal() : l2_policy_evict_last();
     const uint64_t pol_stream = (a.dbg & 512) ? l2_policy_evict_normal() : l2_policy_evict_first();
 
+    // per-step operands (ordinary launch: the StepArgs fields; persistent rollout: derived from the bases per step)
+    // PERSIST = false (one launch per step): read straight from the kernel parameters
+    DStep* stp = reinterpret_cast<DStep*>(smem + D_TSLOT + 16);
+#define STP(f) (PERSIST ? stp->f : a.f)
+
     // one thread: draw the next sequence number and resolve its metadata (3 dependent loads of small tables)
     auto fetch_meta = [&](int k) {
         // first tile: static, CTA-major (a batch with fewer tiles than pipelines is spread one tile per SM, and the
         // launch starts without a burst of atomics); later tiles: dynamic ticket
         const int first = (a.dbg & 524288) ? NP * (int)blockIdx.x + half          // A/B: adjacent first tiles per CTA
                                            : (int)blockIdx.x + half * (int)gridDim.x;
-        int seq = k == 0 ? first : (a.counter ? NP * (int)gridDim.x + atomicAdd(a.counter, 1) : first + NP * k * (int)gridDim.x);
+        int seq = k == 0 ? first : (STP(counter) ? NP * (int)gridDim.x + atomicAdd(STP(counter), 1) : first + NP * k * (int)gridDim.x);
         if ((a.dbg & 2048) && half != 0) seq = n_tiles;               // timing experiment: one pipeline per SM
         DTileMeta m;
         m.seq = seq; m.rowptr = nullptr; m.colidx = nullptr;
@@ -860,7 +887,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
 
     umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
     if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
-    if (t == 0) { umma::mbar_init(mbar, 1); fetch_meta(0); }
+    if (t == 0) umma::mbar_init(mbar, 1);
     umma::fence_before_sync();
     if (tid < H) bs[tid] = a.p.lin_b[tid];
     if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
@@ -880,11 +907,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     const int erow = q * (TR / 4) + lane;                             // tile row this thread owns in the epilogues
     uint32_t phase = 0;
     int kfetch = 1;
+    const int n_steps = PERSIST ? max(a.n_steps, 1) : 1;
 
     // S_k rows of the tile (4 rows x 16 B per thread)
     float4 sreg[4];
     auto load_s = [&](int tile0, int nrows) {
-        const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+        const float* src = STP(y_in) + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             sreg[i] = (hw + RSTEP * i < nrows) ? ldg4_hint(src + (size_t)i * RSTEP * H, pol_stream) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -892,6 +920,31 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
 #define GN_TICK(i) if (a.tbuf && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
+#pragma unroll 1
+    for (int step = 0; step < n_steps; ++step) {
+    if (PERSIST) {
+    if (tid == 0) {
+        DStep d;
+        d.y_in = a.y_in; d.y_out = a.y_out; d.ip_in = a.ip_in; d.ip_out = a.ip_out;
+        d.probs = a.probs; d.counter = a.counter; d.tm = &a.tm_ip_out; d.dt = a.dt;
+        if (a.n_steps > 0) {                              // persistent rollout: operands of Euler step ks
+            const int ks = a.k0 + step;
+            const size_t plane3 = 3 * (size_t)M * H;
+            d.y_in = a.traj ? a.traj + (size_t)ks * plane3 : a.st[ks & 1];
+            d.y_out = a.traj ? a.traj + (size_t)(ks + 1) * plane3 : a.st[(ks + 1) & 1];
+            d.ip_in = a.ipb[ks & 1]; d.ip_out = a.ipb[(ks + 1) & 1];
+            d.probs = ks > 0 ? a.probs_base + (size_t)ks * M * 3 : nullptr;
+            d.dt = a.dt_dev[ks];
+            d.counter = a.counters ? a.counters + ks + 1 : nullptr;
+            d.tm = &a.tm_ipb[(ks + 1) & 1];
+        }
+        *stp = d;
+    }
+    __syncthreads();
+    }
+    if (t == 0) fetch_meta(0);
+    kfetch = 1;
+    HSYNC();
     for (;;) {
         const DTileMeta m = *meta;                                    // written before the last barrier passed
         if (m.seq >= n_tiles) break;
@@ -963,7 +1016,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile; row pairs handed out dynamically
         //      (the next pair's ticket is drawn before the current pair's loads, so its latency is hidden)
         {
-            const float* lane_base = a.ip_in + (size_t)i_row0 * H + 4 * l;
+            const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
             const int zrow = M - i_row0;                     // the all-zero row that follows the I' rows
             if (single) {
                 int p = 0;
@@ -999,7 +1052,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                         e0 = I.rowptr[g - row0];
                         deg = I.rowptr[g - row0 + 1] - e0;
                     }
-                    const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
+                    const float4 acc = gather_row(STP(ip_in), ci, e0, deg, row0, l, lane);
                     sts4(Xs, off0 + it * PASS, acc);
                 }
             }
@@ -1016,14 +1069,14 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                 s = make_float4(1.f, 1.f, 1.f, 1.f); iv = s; rv = s; ipo = s;
                 if (rr < nrows && !(a.dbg & 4)) {
                     const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                    s = ldg4_hint(a.y_in + off, pol_stream);
-                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
-                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
-                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
+                    s = ldg4_hint(STP(y_in) + off, pol_stream);
+                    iv = ldg4_hint(STP(y_in) + plane + off, pol_stream);
+                    rv = ldg4_hint(STP(y_in) + 2 * plane + off, pol_stream);
+                    ipo = ldg4_hint(STP(ip_in) + off, pol_keep);
                 }
             };
             load_own(0);
-            const bool dec = a.probs != nullptr && !(a.dbg & 8192);
+            const bool dec = STP(probs) != nullptr && !(a.dbg & 8192);
             const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
             const float4 w30 = *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l), w31 = *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l),
                          w32 = *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l), w33 = *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l);
@@ -1036,7 +1089,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
                     const float4 acc = lds4(Xs, off0 + it * PASS);
                     const float4 sp = lds4(Ls, off0 + it * PASS);
-                    const float nbe = -bg_s[rr], ga = bg_s[TR + rr], dt = a.dt;
+                    const float nbe = -bg_s[rr], ga = bg_s[TR + rr], dt = STP(dt);
                     float4 sn, in_, rn;
 #define GN_COMP(c)                                                                  \
     {                                                                               \
@@ -1050,9 +1103,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
 #undef GN_COMP
                     if (!(a.dbg & 4096)) {
-                    stg4_hint(a.y_out + off, sn, pol_stream);
-                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
-                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
+                    stg4_hint(STP(y_out) + off, sn, pol_stream);
+                    stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
+                    stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
                     }
                     float4 hi, lo;
                     umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
@@ -1076,7 +1129,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         }
         GN_TICK(3)
         float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
-        if (a.probs != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
+        if (STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
         umma::fence_proxy_async();
         HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         GN_TICK(4)
@@ -1085,7 +1138,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         if (do_g2 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
         if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
-        if (a.probs != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
+        if (STP(probs) != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
             const float4 hR = *reinterpret_cast<const float4*>(hr_s + 4 * t);
             const float4 b3v = *reinterpret_cast<const float4*>(small);
@@ -1098,7 +1151,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             const float eS = ex2_approx((oS - mx) * 1.4426950408889634f), eI = ex2_approx((oI - mx) * 1.4426950408889634f),
                         eR = ex2_approx((oR - mx) * 1.4426950408889634f);
             const float inv = rcp_approx(eS + eI + eR);
-            float* pr = a.probs + (size_t)(tile0 + t) * 3;
+            float* pr = STP(probs) + (size_t)(tile0 + t) * 3;
             pr[0] = eS * inv; pr[1] = eI * inv; pr[2] = eR * inv;
         }
         if (do_g2) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }
@@ -1133,13 +1186,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         //      overwritten once the bulk group has finished READING shared memory. Otherwise: coalesced LSU stores.
         if (NP == 2 && a.use_tma) {
             if (t == 0 && !(a.dbg & 16384)) {
-                tma_store_2d(&a.tm_ip_out, Ls, 0, tile0, pol_stream);
-                tma_store_2d(&a.tm_ip_out, Ls + C::KBLK, 32, tile0, pol_stream);
+                tma_store_2d((PERSIST ? stp->tm : &a.tm_ip_out), Ls, 0, tile0, pol_stream);
+                tma_store_2d((PERSIST ? stp->tm : &a.tm_ip_out), Ls + C::KBLK, 32, tile0, pol_stream);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
         } else {
-            float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
+            float* dst = STP(ip_out) + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (hw + RSTEP * i < nrows && !(a.dbg & 16384)) stg4_hint(dst + (size_t)i * RSTEP * H, lds4(Ls, off0 + i * PASS), pol_stream);
@@ -1147,10 +1200,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         HSYNC();                                                                // S5
         GN_TICK(6)
     }
+    if (step + 1 < n_steps) {
+        // every I' / state row of this step must be complete and visible before any pipeline gathers it: the TMA
+        // stores are awaited in full (not only their shared-memory reads), then the grid barrier (its gpu-scope fence
+        // also invalidates L1, which still holds lines of the ping-pong buffers from two steps ago)
+        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+    }
+    }
     if (a.tbuf && tid == 0)
         for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
 #undef GN_TICK
 #undef HSYNC
+#undef STP
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(*tslot, C::TMEM_COLS);
@@ -1575,12 +1638,20 @@ template <bool FAST, int NP>
 static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     static bool configured[64] = {false};
     if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
         configured[b->device & 63] = true;
     }
     const int units = (NP == 2 ? 1 : 2) * b->n_tiles;
     const int grid = std::min(units, b->sm_count);          // small batches: one tile per SM before a second pipeline is used
-    step_dual_kernel<FAST, NP><<<grid, D_THREADS, PipeCfg<NP>::TOTAL, stream>>>(a);
+    if (a.n_steps > 0) {                                    // persistent rollout: all CTAs co-resident (1 per SM), grid barriers inside
+        void* params[] = {const_cast<StepArgs*>(&a)};
+        GN_CUDA(cudaLaunchCooperativeKernel((const void*)step_dual_kernel<FAST, NP, true>, dim3(grid), dim3(D_THREADS), params,
+                                            (size_t)PipeCfg<NP>::TOTAL, stream));
+        gnode::g_launches++;
+        return GNODE_OK;
+    }
+    step_dual_kernel<FAST, NP, false><<<grid, D_THREADS, PipeCfg<NP>::TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;
 }
@@ -1679,6 +1750,7 @@ extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) 
     const size_t M = (size_t)b->M;
     size_t bytes = 2 * align_up(M * sizeof(float), 256);          // beta, gamma
     bytes += 4096;                                                // tile-scheduler counters (one int per launch)
+    bytes += 4096;                                                // device copy of the step sizes (persistent rollout)
     bytes += 2 * align_up((M + 1) * H * sizeof(float), 256);      // I' ping-pong (+ one all-zero row each)
     bytes += align_up(M * 4 * sizeof(float), 256);                // hid_i: linear3 pre-activations of the I block
     if (!with_traj) bytes += 2 * align_up(3 * M * H * sizeof(float), 256);  // state ping-pong
@@ -1703,6 +1775,7 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     float* beta = (float*)ws;  ws += align_up(M * sizeof(float), 256);
     float* gamma = (float*)ws; ws += align_up(M * sizeof(float), 256);
     int* counters = (int*)ws;  ws += 4096;
+    float* dt_dev = (float*)ws; ws += 4096;
     GN_CUDA(cudaMemsetAsync(counters, 0, 4096, stream));
     float* ip[2];
     ip[0] = (float*)ws; ws += align_up((M + 1) * H * sizeof(float), 256);
@@ -1739,6 +1812,29 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     a.hid_i = dual ? hid_i : nullptr;
     int rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
+    a.n_steps = 0; a.k0 = 0;
+    // Persistent rollout: ONE cooperative launch runs all T-1 Euler steps with a grid barrier between them (no per-step
+    // launch, weight operands and TMEM stay resident).
+    // Default: batches of up to 16 tiles per pipeline (~600k rows), where a launch per step costs >= 2 % ; larger batches
+    // keep one launch per step (the persistent variant reads its per-step operands from shared memory: -1 % there).
+    // GNODE_PERSISTENT=1 / 0 forces it on / off.
+    static const int persistent_mode = getenv("GNODE_PERSISTENT") ? atoi(getenv("GNODE_PERSISTENT")) : -1;
+    const bool persistent_ok = persistent_mode < 0 ? b->n_tiles <= 32 * b->sm_count : persistent_mode != 0;
+    int coop = 0;
+    if (dual && persistent_ok && T > 2 && T - 1 <= 1023 && !(a.dbg & 64))
+        GN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device));
+    if (coop) {
+        GN_CUDA(cudaMemcpyAsync(dt_dev, dt_host, sizeof(float) * (size_t)(T - 1), cudaMemcpyHostToDevice, stream));
+        a.n_steps = T - 1; a.k0 = 0;
+        a.traj = traj; a.st[0] = st[0]; a.st[1] = st[1];
+        a.ipb[0] = ip[0]; a.ipb[1] = ip[1];
+        a.probs_base = probs; a.dt_dev = dt_dev; a.counters = counters;
+        a.use_tma = have_tma ? 1 : 0;
+        if (have_tma) { a.tm_ipb[0] = tm_ip[0]; a.tm_ipb[1] = tm_ip[1]; }
+        a.y_in = state(0); a.y_out = state(1); a.ip_in = ip[0]; a.ip_out = ip[1]; a.probs = nullptr; a.dt = dt_host[0];
+        rc = launch_step<MODE_STEP>(b, a, stream);
+        if (rc) return rc;
+    } else
     for (int k = 0; k + 1 < T; ++k) {
         a.y_in = state(k); a.y_out = state(k + 1);
         a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
@@ -1769,7 +1865,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr; a.use_tma = 0;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr; a.use_tma = 0; a.n_steps = 0;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;
