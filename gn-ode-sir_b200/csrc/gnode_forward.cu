@@ -16,6 +16,7 @@
 #include <cuda.h>          // CUtensorMap (type and enums only: the encoder is resolved through the runtime, no libcuda link)
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "gnode_common.cuh"
 #include "gnode_tile.cuh"
@@ -41,6 +42,8 @@ struct StepArgs {
     int64_t ldx;
     float* probs;         // [M][3] slice of the produced state (dual kernel: of the INPUT state), or null
     float* hid_i;         // [M][4] linear3 pre-activations (no bias) of the I block: ENCODE writes I_0's, the dual step kernel updates in place; or null
+    float* hid_r;         // [M][4] inference without an R plane (dual kernel, RF): linear3 pre-activations of the R block, carried by
+                          // linearity (hid(R_{k+1}) = hid(R_k) + dt gamma W3 I'_k); ENCODE writes R_0's; null = R is a full state plane
     float dt;
     long long* tbuf;      // phase timing accumulators (debug, env GNODE_DBG bit 7) or null
     int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
@@ -80,7 +83,8 @@ constexpr int VAR_TC = 1, VAR_FASTSIG = 2;
 // decoder + softmax of one row held 4 channels per lane by a half-warp
 // (linear3 -> ReLU -> linearS2 -> softmax over {S,I,R}; ode_nn_ngraph_sim.py:172-187)
 __device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const float* W3s, const float* small,
-                                           int l, bool valid, float* probs_row, float* hid_i_row = nullptr) {
+                                           int l, bool valid, float* probs_row, float* hid_i_row = nullptr,
+                                           float* hid_r_row = nullptr, const float* hid_r_in = nullptr) {
     float v[12];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -92,6 +96,11 @@ __device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const f
 #pragma unroll
         for (int m = 0; m < 12; ++m) v[m] += __shfl_xor_sync(0xffffffffu, v[m], off);
     if (l == 0 && valid && hid_i_row != nullptr) *reinterpret_cast<float4*>(hid_i_row) = make_float4(v[4], v[5], v[6], v[7]);
+    if (l == 0 && valid && hid_r_row != nullptr) *reinterpret_cast<float4*>(hid_r_row) = make_float4(v[8], v[9], v[10], v[11]);
+    if (l == 0 && valid && hid_r_in != nullptr) {      // R is carried as its four hidden pre-activations only
+        const float4 h = *reinterpret_cast<const float4*>(hid_r_in);
+        v[8] = h.x; v[9] = h.y; v[10] = h.z; v[11] = h.w;
+    }
     if (l == 0 && valid && probs_row != nullptr) {
         const float* b3 = small; const float* w2 = small + 4; const float b2 = small[8];
         float o[3];
@@ -263,9 +272,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
                     stg4_stream(a.y_out + 2 * plane + off, r0);
                 }
                 sts4(Xs, sw_off(rr, l), i0);
-                if (a.probs != nullptr || a.hid_i != nullptr)
+                if (a.probs != nullptr || a.hid_i != nullptr || a.hid_r != nullptr)
                     decode_row(s0, i0, r0, W3s, small, l, valid, a.probs ? a.probs + (size_t)(valid ? g : 0) * 3 : nullptr,
-                               a.hid_i ? a.hid_i + (size_t)(valid ? g : 0) * 4 : nullptr);
+                               a.hid_i ? a.hid_i + (size_t)(valid ? g : 0) * 4 : nullptr,
+                               a.hid_r ? a.hid_r + (size_t)(valid ? g : 0) * 4 : nullptr);
             }
             __syncthreads();
         }
@@ -818,7 +828,7 @@ struct DStep {
     float dt;
 };
 
-template <bool FAST, int NP, bool PERSIST>
+template <bool FAST, int NP, bool PERSIST, bool RF>
 __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_constant__ StepArgs a) {
     using C = PipeCfg<NP>;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
@@ -1013,18 +1023,25 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         umma::fence_before_sync();
         HSYNC();                                                                // S2
         GN_TICK(1)
-        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile; row pairs handed out dynamically
-        //      (the next pair's ticket is drawn before the current pair's loads, so its latency is hidden)
+        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile
         {
             const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
             const int zrow = M - i_row0;                     // the all-zero row that follows the I' rows
             if (single) {
-                int p = 0;
-                if (lane == 0) p = atomicAdd(row_ctr, 1);
-                p = __shfl_sync(0xffffffffu, p, 0);
+                // row pairs: strided over the warps when the tile's CSR slice fits the staged window (no hub in the tile:
+                // +1.3 % over tickets, same box), shared-memory tickets for hub tiles so that a long row does not leave
+                // the other warps idle (GNODE_DBG bit 20: tickets always)
+                const bool static_rows = m.ecnt <= C::CAP && (a.dbg & 1048576) == 0;
+                int p = 0, sj = 1;
+                if (static_rows) p = warp;
+                else {
+                    if (lane == 0) p = atomicAdd(row_ctr, 1);
+                    p = __shfl_sync(0xffffffffu, p, 0);
+                }
                 while (p < TR / 2) {
                     int pn = 0;
-                    if (lane == 0) pn = atomicAdd(row_ctr, 1);
+                    if (static_rows) { pn = warp + (PT / 32) * sj; ++sj; }
+                    else if (lane == 0) pn = atomicAdd(row_ctr, 1);
                     const int rr = 2 * p + (lane >> 4);
                     int e_rel = 0, deg = 0;
                     if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
@@ -1035,7 +1052,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     else
                         acc = gather_smem_z(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
                     sts4(Xs, C::sw(rr, l), acc);
-                    p = __shfl_sync(0xffffffffu, pn, 0);
+                    p = static_rows ? pn : __shfl_sync(0xffffffffu, pn, 0);
                 }
             } else {                                         // tile spans several (small) instances
                 int inst = m.inst0;
@@ -1071,12 +1088,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
                     s = ldg4_hint(STP(y_in) + off, pol_stream);
                     iv = ldg4_hint(STP(y_in) + plane + off, pol_stream);
-                    rv = ldg4_hint(STP(y_in) + 2 * plane + off, pol_stream);
+                    if (!RF) rv = ldg4_hint(STP(y_in) + 2 * plane + off, pol_stream);
                     ipo = ldg4_hint(STP(ip_in) + off, pol_keep);
                 }
             };
             load_own(0);
-            const bool dec = STP(probs) != nullptr && !(a.dbg & 8192);
+            const bool dec = (RF || STP(probs) != nullptr) && !(a.dbg & 8192);
             const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
             const float4 w30 = *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l), w31 = *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l),
                          w32 = *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l), w33 = *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l);
@@ -1105,14 +1122,15 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     if (!(a.dbg & 4096)) {
                     stg4_hint(STP(y_out) + off, sn, pol_stream);
                     stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
-                    stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
+                    if (!RF) stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
                     }
                     float4 hi, lo;
                     umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
                     sts4(Xs, off0 + it * PASS, hi);
                     sts4(Ls, off0 + it * PASS, lo);
-                    if (dec) {                                   // partial linear3 products of R_k (this lane's 4 channels)
-                        hv0 = dot4(rv, w30); hv1 = dot4(rv, w31); hv2 = dot4(rv, w32); hv3 = dot4(rv, w33);
+                    if (dec) {                                   // partial linear3 products of R_k (RF: of I'_k) over this lane's 4 channels
+                        const float4 dv = RF ? ipo : rv;
+                        hv0 = dot4(dv, w30); hv1 = dot4(dv, w31); hv2 = dot4(dv, w32); hv3 = dot4(dv, w33);
                     }
                 }
                 if (it + 1 < 4) load_own(it + 1);
@@ -1129,7 +1147,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         }
         GN_TICK(3)
         float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
+        float4 hRg = hI;                                 // RF: hid(R_k) of row t
         if (STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
+        if (RF && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
         umma::fence_proxy_async();
         HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         GN_TICK(4)
@@ -1138,9 +1158,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         if (do_g2 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
         if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
+        if (RF && t < nrows) {
+            // R_{k+1} = R_k + dt gamma I'_k is linear and R feeds nothing but the decoder's linear3: the row carries
+            // hid(R) = W3 R (4 floats) instead of the 64-float R plane; hr_s holds W3 I'_k of the row
+            const float4 c = *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            const float g = __fmul_rn(STP(dt), bg_s[TR + t]);
+            *reinterpret_cast<float4*>(a.hid_r + (size_t)(tile0 + t) * 4) =
+                make_float4(fmaf(g, c.x, hRg.x), fmaf(g, c.y, hRg.y), fmaf(g, c.z, hRg.z), fmaf(g, c.w, hRg.w));
+        }
         if (STP(probs) != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
-            const float4 hR = *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            const float4 hR = RF ? hRg : *reinterpret_cast<const float4*>(hr_s + 4 * t);
             const float4 b3v = *reinterpret_cast<const float4*>(small);
             const float4 w2v = *reinterpret_cast<const float4*>(small + 4);
             const float b2v = small[8];
@@ -1221,7 +1249,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
 
 // Decoder + softmax of one stored state (the last grid point of the dual-kernel rollout): probs = softmax over
 // {S, I, R} of linearS2(relu(linear3(.)))  (ode_nn_ngraph_sim.py:170-188). Half-warp per row.
-__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ y, float* __restrict__ probs, int M, const gnode_params_t p) {
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ y, float* __restrict__ probs, int M, const gnode_params_t p,
+                                                     const float* __restrict__ hid_r) {
     __shared__ __align__(16) float W3s[4 * H];
     __shared__ float small[16];
     const int tid = threadIdx.x, l = tid & 15;
@@ -1236,9 +1265,11 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ y
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), i = s, r = s;
         if (valid) {
             const size_t off = (size_t)g * H + 4 * l;
-            s = ldg4_stream(y + off); i = ldg4_stream(y + plane + off); r = ldg4_stream(y + 2 * plane + off);
+            s = ldg4_stream(y + off); i = ldg4_stream(y + plane + off);
+            if (hid_r == nullptr) r = ldg4_stream(y + 2 * plane + off);
         }
-        decode_row(s, i, r, W3s, small, l, valid, probs + (size_t)(valid ? g : 0) * 3);
+        decode_row(s, i, r, W3s, small, l, valid, probs + (size_t)(valid ? g : 0) * 3, nullptr, nullptr,
+                   hid_r ? hid_r + (size_t)(valid ? g : 0) * 4 : nullptr);
     }
 }
 
@@ -1634,24 +1665,24 @@ static int launch_step_ws(const gnode_batch* b, const StepArgs& a, cudaStream_t 
     return GNODE_OK;
 }
 
-template <bool FAST, int NP>
+template <bool FAST, int NP, bool RF>
 static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     static bool configured[64] = {false};
     if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
-        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP, false, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_dual_kernel<FAST, NP, true, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NP>::TOTAL));
         configured[b->device & 63] = true;
     }
     const int units = (NP == 2 ? 1 : 2) * b->n_tiles;
     const int grid = std::min(units, b->sm_count);          // small batches: one tile per SM before a second pipeline is used
     if (a.n_steps > 0) {                                    // persistent rollout: all CTAs co-resident (1 per SM), grid barriers inside
         void* params[] = {const_cast<StepArgs*>(&a)};
-        GN_CUDA(cudaLaunchCooperativeKernel((const void*)step_dual_kernel<FAST, NP, true>, dim3(grid), dim3(D_THREADS), params,
+        GN_CUDA(cudaLaunchCooperativeKernel((const void*)step_dual_kernel<FAST, NP, true, RF>, dim3(grid), dim3(D_THREADS), params,
                                             (size_t)PipeCfg<NP>::TOTAL, stream));
         gnode::g_launches++;
         return GNODE_OK;
     }
-    step_dual_kernel<FAST, NP, false><<<grid, D_THREADS, PipeCfg<NP>::TOTAL, stream>>>(a);
+    step_dual_kernel<FAST, NP, false, RF><<<grid, D_THREADS, PipeCfg<NP>::TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;
 }
@@ -1664,6 +1695,17 @@ static int step_kernel_choice() {
     return g_step_kernel;
 }
 
+// Inference (no stored trajectory) with the default dual kernel carries R as hid(R) = W3 R, four floats per row, instead
+// of a 64-float state plane: R_{k+1} = R_k + dt gamma I'_k is linear in I' and R feeds nothing but the decoder's linear3
+// (ode_nn_ngraph_sim.py:77,172-176), so hid(R_{k+1}) = hid(R_k) + dt gamma (W3 I'_k). 512 of the 2060 algorithmic bytes
+// per node-step are not moved; the roofline denominator stays 2060. GNODE_R_STATE=full / gnode_set_r_state(0)
+// keeps the R plane (bitwise the training forward); training always stores R (the decoder's weight gradient needs it).
+static int g_r_state = -1;
+static int r_state_choice() {
+    if (g_r_state < 0) { const char* e = getenv("GNODE_R_STATE"); g_r_state = (e && (!strcmp(e, "full") || !strcmp(e, "0"))) ? 0 : 1; }
+    return g_r_state;
+}
+
 // the dual kernel emits probs[k] of its INPUT state and needs the hid_i side buffer (tensor-core variants only)
 static bool use_dual() { return (current_variant() & VAR_TC) && step_kernel_choice() >= 3; }
 
@@ -1671,8 +1713,9 @@ template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
     if (MODE == MODE_STEP && use_dual()) {
-        if (step_kernel_choice() == 4) return (var & VAR_FASTSIG) ? launch_step_dual<true, 4>(b, a, stream) : launch_step_dual<false, 4>(b, a, stream);
-        return (var & VAR_FASTSIG) ? launch_step_dual<true, 2>(b, a, stream) : launch_step_dual<false, 2>(b, a, stream);
+        if (step_kernel_choice() == 4) return (var & VAR_FASTSIG) ? launch_step_dual<true, 4, false>(b, a, stream) : launch_step_dual<false, 4, false>(b, a, stream);
+        if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
+        return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, false>(b, a, stream) : launch_step_dual<false, 2, false>(b, a, stream);
     }
     if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 2)
         return (var & VAR_FASTSIG) ? launch_step_ws<true>(b, a, stream) : launch_step_ws<false>(b, a, stream);
@@ -1734,6 +1777,12 @@ extern "C" int gnode_set_step_kernel(int kernel) {
     return GNODE_OK;
 }
 extern "C" int gnode_get_step_kernel(void) { return step_kernel_choice(); }
+extern "C" int gnode_set_r_state(int hidden) {
+    if (hidden < 0 || hidden > 1) { set_error("gnode_set_r_state: 0 = full R plane, 1 = hidden pre-activations only"); return GNODE_ERR_ARG; }
+    g_r_state = hidden;
+    return GNODE_OK;
+}
+extern "C" int gnode_get_r_state(void) { return r_state_choice(); }
 extern "C" int gnode_debug_phase_cycles(long long* out8) {
     if (!out8) return GNODE_ERR_ARG;
     for (int i = 0; i < 8; ++i) out8[i] = 0;
@@ -1752,7 +1801,7 @@ extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) 
     bytes += 4096;                                                // tile-scheduler counters (one int per launch)
     bytes += 4096;                                                // device copy of the step sizes (persistent rollout)
     bytes += 2 * align_up((M + 1) * H * sizeof(float), 256);      // I' ping-pong (+ one all-zero row each)
-    bytes += align_up(M * 4 * sizeof(float), 256);                // hid_i: linear3 pre-activations of the I block
+    bytes += 2 * align_up(M * 4 * sizeof(float), 256);            // hid_i, hid_r: linear3 pre-activations of the I / R block
     if (!with_traj) bytes += 2 * align_up(3 * M * H * sizeof(float), 256);  // state ping-pong
     return bytes;
 }
@@ -1783,6 +1832,7 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     GN_CUDA(cudaMemsetAsync(ip[0] + M * H, 0, H * sizeof(float), stream));      // row M: the zero row padded gather slots read
     GN_CUDA(cudaMemsetAsync(ip[1] + M * H, 0, H * sizeof(float), stream));
     float* hid_i = (float*)ws; ws += align_up(M * 4 * sizeof(float), 256);
+    float* hid_r = (float*)ws; ws += align_up(M * 4 * sizeof(float), 256);
     float* st[2] = {nullptr, nullptr};
     if (!traj) {
         st[0] = (float*)ws; ws += align_up(3 * M * H * sizeof(float), 256);
@@ -1810,6 +1860,8 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     CUtensorMap tm_ip[2];
     const bool have_tma = dual && !(a.dbg & 32768) && encode_rows_map(&tm_ip[0], ip[0], M) && encode_rows_map(&tm_ip[1], ip[1], M);
     a.hid_i = dual ? hid_i : nullptr;
+    const bool rfree = dual && !traj && T > 1 && step_kernel_choice() == 3 && r_state_choice() == 1;
+    a.hid_r = rfree ? hid_r : nullptr;
     int rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
     a.n_steps = 0; a.k0 = 0;
@@ -1848,7 +1900,7 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     }
     if (dual && T > 1) {                                   // the last grid state
         const int grid = (int)std::min<int64_t>(((int64_t)M + 15) / 16, (int64_t)b->sm_count * 16);
-        decode_kernel<<<grid, 256, 0, stream>>>(state(T - 1), probs + (size_t)(T - 1) * M * 3, (int)M, *p);
+        decode_kernel<<<grid, 256, 0, stream>>>(state(T - 1), probs + (size_t)(T - 1) * M * 3, (int)M, *p, a.hid_r);
         GN_LAUNCH_CHECK();
     }
     return GNODE_OK;
@@ -1865,7 +1917,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);
-    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr; a.use_tma = 0; a.n_steps = 0;
+    a.x = nullptr; a.ldx = 0; a.probs = nullptr; a.hid_i = nullptr; a.hid_r = nullptr; a.dt = 0.f; a.counter = nullptr; a.dbg = 0; a.tbuf = nullptr; a.use_tma = 0; a.n_steps = 0;
     a.y_in = y; a.y_out = nullptr; a.ip_in = nullptr; a.ip_out = scratch;
     int rc = launch_step<MODE_IP>(b, a, stream);       // I' of every row first (grid-wide dependency)
     if (rc) return rc;

@@ -83,6 +83,14 @@ int gnode_get_variant(void);
  * within the parity tolerance. */
 int gnode_set_step_kernel(int kernel);
 int gnode_get_step_kernel(void);
+/* How inference rollouts (traj == NULL, default step kernel) carry the R block. 1 (default) = as its four linear3
+ * pre-activations hid(R) = W3 R per row: R_{k+1} = R_k + dt gamma I'_k (ode_nn_ngraph_sim.py:77 + the Euler update)
+ * is linear in I' and R feeds only the decoder's linear3 (:172-176), so hid(R_{k+1}) = hid(R_k) + dt gamma W3 I'_k
+ * and the 64-float R plane is neither read nor written (512 B per node-step less traffic; probabilities agree with
+ * the full-plane path to fp32 rounding, ~1e-7). 0 = full R plane, bitwise the training forward. Env GNODE_R_STATE=full
+ * selects 0. Training (traj != NULL) always stores R. */
+int gnode_set_r_state(int hidden);
+int gnode_get_r_state(void);
 /* debug: per-phase SM-cycle sums of the step kernel collected while env GNODE_DBG has bit 7 set; resets them */
 int gnode_debug_phase_cycles(long long* out8);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
