@@ -33,6 +33,11 @@ import torch          # noqa: E402
 H = 64
 MAXTIME, DELTAT = 20, 0.5
 ALGO_BYTES_PER_NODE_STEP = 2060.0      # SURVEY 8d / BASELINE.md section 3 (fixed denominator)
+R_STATE_NOTE = {
+    1: "inference carries R as hid(R) = W3 R (4 floats per row, exact by linearity of R' = gamma I'); the 64-float R plane is "
+       "neither read nor written, i.e. 512 of the 2060 algorithmic bytes per node-step are not moved -- the roofline denominator "
+       "stays 2060 B (SURVEY 8d); GNODE_R_STATE=full keeps the plane",
+    0: "full 64-float R plane (GNODE_R_STATE=full)"}
 UNIT = "node-steps/s"
 METRIC = "GN-ODE rollout node-steps/s (epinions)"
 
@@ -175,13 +180,14 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, r_state=None):
     name, cfg = WORKLOADS[args.workload]
     return {"workload": "%s rollout inference, H=64, T=40 (maxTime=20, deltaT=0.5), %d trials per GPU (%s)" % (name, args.trials, cfg),
             "trials_per_gpu": args.trials, "global_trials": args.trials * world,
             "nodes": 75879 if args.workload == "epinions" else 2000000,
             "euler_steps": int(len(np.arange(0, MAXTIME, DELTAT)) - 1), "parallelism": "trial-sharded dp%d, graph replicated" % world,
-            "l2_policy": "no flush: per-step working set (state+I' of all trials, >3 GB) exceeds the 126 MB L2"}
+            "l2_policy": "no flush: per-step working set (state+I' of all trials, >3 GB) exceeds the 126 MB L2",
+            "r_state": R_STATE_NOTE[r_state] if r_state is not None else None}
 
 
 def main():
@@ -275,7 +281,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": "gnode::step_dual_kernel (fused Euler step, tcgen05; encoder + final decode launches charged to it)", "launch_ms": step_ms, "rows_per_launch": rows,
-                "algorithmic_bytes_per_node_step": ALGO_BYTES_PER_NODE_STEP, "peak_source": peak_src}
+                "algorithmic_bytes_per_node_step": ALGO_BYTES_PER_NODE_STEP, "peak_source": peak_src,
+                "traffic_source": "profiles/step_kernel_traffic.json (ncu --set full dram bytes per row of the committed capture) x rows"}
     del S, I, R
 
     # ---------------- end-to-end through the public API with host buffers
@@ -343,7 +350,7 @@ def main():
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, int(L.gnode_get_r_state())),
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(out), flush=True)
     if dist is not None:
