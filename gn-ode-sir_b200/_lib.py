@@ -63,11 +63,12 @@ def lib():
     """The loaded library; raises loudly when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("GNODE_B200_LIB", LIB_PATH)      # another build of the same ABI (A/B measurements)
+        if not os.path.exists(path):
             raise RuntimeError(
                 "libgnode_b200.so is missing (%s). Build it with `python -c \"import __graft_entry__ as g; "
-                "g.build()\"`. There is no CPU fallback for the GN-ODE rollout." % LIB_PATH)
-        handle = ctypes.CDLL(LIB_PATH)
+                "g.build()\"`. There is no CPU fallback for the GN-ODE rollout." % path)
+        handle = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
