@@ -116,7 +116,6 @@ WORKLOADS = {
 
 def build_workload(trials, trial_offset, workload="epinions"):
     from gn_ode_sir_b200 import synth
-    from oracle import gnode_oracle as orc      # only for the shared synthetic-input recipe
     A = synth.epinions_standin(seed=0) if workload == "epinions" else synth.ba_stress(seed=0)
     N = A.shape[0]
     x = torch.zeros(trials, N, 3 + H, dtype=torch.float32)
@@ -128,13 +127,15 @@ def build_workload(trials, trial_offset, workload="epinions"):
         x[b, seeds, 0] = 0.0
         x[b, seeds, 1] = 1.0
         x[b, :, 3], x[b, :, 4] = beta, gamma
-    return A, x, orc
+    return A, x
 
 
-def cpu_reference_sample(A, orc, trials, n_points, repeats=1):
+def cpu_reference_sample(A, trials, n_points, repeats=1):
     """Times the oracle port of the reference's CPU path (torch ops, per-step host-side
-    block_diag rebuild as at ode_nn_ngraph_sim.py:68-71) on a bounded sample."""
+    block_diag rebuild as at ode_nn_ngraph_sim.py:68-71) on a bounded sample. The only place
+    where bench.py touches oracle/ (cpu_baseline leg and the --impl reference arm)."""
     import scipy.sparse
+    from oracle import gnode_oracle as orc
     N = A.shape[0]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -160,13 +161,13 @@ def cpu_reference_sample(A, orc, trials, n_points, repeats=1):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    A, _, orc = build_workload(0, 0, args.workload)
+    A, _ = build_workload(0, 0, args.workload)
     for _ in range(args.warmup):
-        cpu_reference_sample(A, orc, 1, 3)
+        cpu_reference_sample(A, 1, 3)
     vals, times = [], []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        v, cores, sample = cpu_reference_sample(A, orc, args.ref_trials, args.ref_points)
+        v, cores, sample = cpu_reference_sample(A, args.ref_trials, args.ref_points)
         times.append(time.perf_counter() - t0)
         vals.append(v)
     value = float(np.mean(vals))
@@ -228,7 +229,7 @@ def main():
     gn.build_library()
     L = _lib.lib()
 
-    A, x_host, orc = build_workload(args.trials, rank * args.trials, args.workload)
+    A, x_host = build_workload(args.trials, rank * args.trials, args.workload)
     N = A.shape[0]
     T = len(np.arange(0, MAXTIME, DELTAT))
     torch.manual_seed(0)
@@ -344,7 +345,7 @@ def main():
     # ---------------- CPU baseline (oracle port of the reference's CPU path), rank 0, N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_reference_sample(A, orc, args.ref_trials, args.ref_points)
+        v, cores, sample = cpu_reference_sample(A, args.ref_trials, args.ref_points)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:

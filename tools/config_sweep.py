@@ -6,7 +6,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, scipy.sparse, torch
 import gn_ode_sir_b200 as gn
 from gn_ode_sir_b200 import synth
-from oracle import gnode_oracle as orc
 
 dev = torch.device("cuda:0")
 
