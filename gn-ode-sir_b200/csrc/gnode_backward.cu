@@ -25,6 +25,7 @@
 // Parameter-gradient partial sums live in per-CTA slots (no atomics: bitwise reproducible) and are
 // folded by reduce_partials_kernel at the end.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gnode_common.cuh"
 #include "gnode_tile.cuh"
@@ -153,6 +154,8 @@ __device__ __forceinline__ void decoder_backward_row(const float4 (&c)[3], const
 }
 
 // ---------------------------------------------------------------- K2
+// (3 CTAs per SM at 80 registers; 2 CTAs at 128 registers without spills, and issuing the own-row loads before the
+// gather, measured no better: profiles/r1e_ab_backward.log)
 __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a) {
     __shared__ float W3s[4 * H];
     __shared__ float small[12];
@@ -182,9 +185,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a
         const size_t off = (size_t)(valid ? g : 0) * H + 4 * l;
         float4 AI = make_float4(0.f, 0.f, 0.f, 0.f);
         float be = 0.f;
+        int row0 = 0, e0 = 0, deg = 0;
+        const int32_t* ci = nullptr;
         if (!a.only_dec) {
-            int row0 = 0, e0 = 0, deg = 0;
-            const int32_t* ci = nullptr;
             if (valid) {
                 int inst = a.bv.tile_inst[g / TILE];                 // owner of the tile's first row, then walk forward
                 while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
@@ -453,6 +456,169 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_vjp_kernel(const BwdArgs a) {
     if (tid < 32) umma::tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------- K3, two CTAs per SM
+// The same work as bwd_vjp_kernel with half the shared memory per CTA: the (gzS, S_j) and (gzI, I_j) pairs of a tile are
+// processed one after the other through ONE gz tile and ONE state tile (96 KB per CTA with the W^T operand), by 256
+// threads, so that two CTAs are resident per SM and the load / FFMA / tensor / read-modify-write phases of one overlap
+// those of the other (bwd_vjp_kernel runs them back to back on one 512-thread CTA: 1.8 TB/s of its 2 KB per row).
+constexpr int K3B_THREADS = 256;
+constexpr int K3B_SM_G = 0, K3B_SM_X = 32768, K3B_SM_WTHI = 65536, K3B_SM_WTLO = K3B_SM_WTHI + H * H * 4,
+              K3B_SM_BAR = K3B_SM_WTLO + H * H * 4, K3B_SM_TOTAL = K3B_SM_BAR + 16 + 1024;
+
+__global__ void __launch_bounds__(K3B_THREADS, 2) bwd_vjp2_kernel(const BwdArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* G = smem + K3B_SM_G;
+    unsigned char* X = smem + K3B_SM_X;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + K3B_SM_BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + K3B_SM_BAR + 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    // B operand of v[r][j] = sum_h gz[r][h] W[h][j]: row n = j, K index = h, i.e. W transposed
+    for (int idx = tid; idx < H * CHUNKS; idx += K3B_THREADS) {
+        const int n = idx >> 4, c4 = idx & 15;
+        const float4 w = make_float4(a.p.lin_w[(4 * c4 + 0) * H + n], a.p.lin_w[(4 * c4 + 1) * H + n],
+                                     a.p.lin_w[(4 * c4 + 2) * H + n], a.p.lin_w[(4 * c4 + 3) * H + n]);
+        float4 hi, lo;
+        umma::tf32_split4(w, hi, lo);
+        sts4(smem + K3B_SM_WTHI, umma::swb_off(n, c4), hi);
+        sts4(smem + K3B_SM_WTLO, umma::swb_off(n, c4), lo);
+    }
+    umma::fence_proxy_async();
+    if (tid < 32) umma::tmem_alloc(tslot, 64);         // one [128 x 64] fp32 accumulator
+    if (tid == 0) umma::mbar_init(mbar, 1);
+    umma::fence_before_sync();
+
+    // weight-gradient accumulators, register-blocked 8 (h) x 4 (j); thread = (row group of 64 rows, h block of 8,
+    // 16-byte column chunk); both parts of a tile add into the same accumulators (vW = gzS^T S + gzI^T I)
+    const int wrg = tid >> 7, whb = (tid >> 4) & 7, wjq = tid & 15;
+    float gw[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gw[i] = 0.f;
+    // bias gradient vb[h] = sum_r gz[r][h]: column sums taken where the gz tile is split (every thread already reads
+    // its 16-byte column chunk c4 = tid & 15 of rows (tid >> 4) + 16 k there), not in the FFMA loop
+    float4 gbv = make_float4(0.f, 0.f, 0.f, 0.f);
+    // FFMA loop addressing: rows are walked in blocks of 8 so that the swizzle term (r & 7) is a compile-time constant
+    const int cg = (2 * whb) & 7, cx = wjq & 7;
+    const unsigned char* Gb = G + ((2 * whb) >> 3) * (TILE * 128) + 64 * wrg * 128;
+    const unsigned char* Xb = X + (wjq >> 3) * (TILE * 128) + 64 * wrg * 128;
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t wthi = umma::smem_u32(smem + K3B_SM_WTHI), wtlo = umma::smem_u32(smem + K3B_SM_WTLO);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TILE;
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            // gz tile (written by bwd_gz_kernel over Sp / AI) and the state tile of this part -> shared memory
+            const float* gsrc = part == 0 ? a.Sp : a.AI;
+            const float* xsrc = a.y + (size_t)part * plane;
+            for (int idx = tid; idx < TILE * CHUNKS; idx += K3B_THREADS) {
+                const int rr = idx >> 4, c4 = idx & 15;
+                const int64_t g = tile0 + rr;
+                const int so = sw_off(rr, c4);
+                if (g < M) {
+                    const size_t go = (size_t)g * H + 4 * c4;
+                    cp_async16(G + so, gsrc + go);
+                    cp_async16(X + so, xsrc + go);
+                } else {
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sts4(G, so, z); sts4(X, so, z);
+                }
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            // ---- vW[h][j] += sum_r gz[r][h] x[r][j] ; vb[h] += sum_r gz[r][h]   (fp32 FFMA)
+#pragma unroll 1
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const unsigned char* gp = Gb + r8 * 1024;
+                const unsigned char* xp = Xb + r8 * 1024;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int og = i * 128 + ((cg ^ i) << 4);
+                    const float4 g0 = *reinterpret_cast<const float4*>(gp + og);
+                    const float4 g1 = *reinterpret_cast<const float4*>(gp + (og ^ 16));
+                    const float4 xv = *reinterpret_cast<const float4*>(xp + i * 128 + ((cx ^ i) << 4));
+                    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int hh = 0; hh < 8; ++hh) {
+                        gw[4 * hh + 0] = fmaf(g[hh], xv.x, gw[4 * hh + 0]); gw[4 * hh + 1] = fmaf(g[hh], xv.y, gw[4 * hh + 1]);
+                        gw[4 * hh + 2] = fmaf(g[hh], xv.z, gw[4 * hh + 2]); gw[4 * hh + 3] = fmaf(g[hh], xv.w, gw[4 * hh + 3]);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- v = gz W on tcgen05: split gz in place (gz tile <- hi, the dead state tile <- lo)
+            for (int idx = tid; idx < TILE * CHUNKS; idx += K3B_THREADS) {
+                const int off = sw_off(idx >> 4, idx & 15);
+                float4 hi, lo;
+                const float4 gz = lds4(G, off);
+                gbv.x += gz.x; gbv.y += gz.y; gbv.z += gz.z; gbv.w += gz.w;
+                umma::tf32_split4(gz, hi, lo);
+                sts4(G, off, hi); sts4(X, off, lo);
+            }
+            umma::fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) umma::issue_split_gemm_to(tmem, mbar, wthi, wtlo, umma::smem_u32(G), umma::smem_u32(X));
+            umma::mbar_wait(mbar, phase);
+            phase ^= 1;
+            umma::fence_after_sync();
+            // ---- a[part] += dt * v: warp (q = lane quarter, ch = 32-column half), thread = tile row (vR = 0)
+            {
+                const int q = warp & 3, ch = warp >> 2;
+                const int64_t g = tile0 + q * 32 + lane;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float v[16];
+                    umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 32 * ch + 16 * cb, v);
+                    if (g < M) {
+                        float* row = a.a + (size_t)part * plane + (size_t)g * H + 32 * ch + 16 * cb;
+#pragma unroll
+                        for (int jj = 0; jj < 16; jj += 4) {
+                            float4 cur = ldg4(row + jj);
+                            cur.x = fmaf(a.dt, v[jj + 0], cur.x); cur.y = fmaf(a.dt, v[jj + 1], cur.y);
+                            cur.z = fmaf(a.dt, v[jj + 2], cur.z); cur.w = fmaf(a.dt, v[jj + 3], cur.w);
+                            stg4(row + jj, cur);
+                        }
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            __syncthreads();
+        }
+    }
+    // fold the two partial sums (row groups) of every output element: red[2][64][64] over the gz tile, red_b[16][64]
+    // over the state tile (the tile loop has ended with a block barrier)
+    {
+        float* red = reinterpret_cast<float*>(G);
+        float* red_b = reinterpret_cast<float*>(X);
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh)
+            *reinterpret_cast<float4*>(red + ((size_t)wrg * H + 8 * whb + hh) * H + 4 * wjq) =
+                make_float4(gw[4 * hh + 0], gw[4 * hh + 1], gw[4 * hh + 2], gw[4 * hh + 3]);
+        *reinterpret_cast<float4*>(red_b + (tid >> 4) * H + 4 * (tid & 15)) = gbv;      // red_b[16 row classes][64]
+        __syncthreads();
+        float* slot = a.part + (size_t)blockIdx.x * LIN_COUNT;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int o = tid * 16 + i;                     // output element (h, j) = (o / 64, o % 64)
+            slot[o] += a.dt * (red[o] + red[H * H + o]);
+        }
+        if (tid < H) {
+            float sb = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) sb += red_b[w * H + tid];
+            slot[H * H + tid] += a.dt * sb;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tmem, 64);
+}
+
 // ---------------------------------------------------------------- K4: encoder backward
 // y0 = relu(c * w1 + b1): d w1[h] = sum a0[h] [y0>0] c ; d b1[h] = sum a0[h] [y0>0]   (c in {S0,I0,R0})
 __global__ void __launch_bounds__(ROW_THREADS) bwd_encoder_kernel(const BwdArgs a) {
@@ -498,6 +664,12 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_slo
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// 2 (default) = bwd_vjp2_kernel (two 256-thread CTAs per SM, parts in sequence), 1 = bwd_vjp_kernel; env GNODE_BWD_VJP
+static int vjp_kernel_choice() {
+    static const int c = getenv("GNODE_BWD_VJP") ? atoi(getenv("GNODE_BWD_VJP")) : 2;
+    return c == 1 ? 1 : 2;
+}
+
 struct BwdPlan {
     int grid_row, grid_tile1, grid_tile3;
     size_t off_a, off_sp, off_ip, off_ai, off_g, off_pdec, off_plin, off_penc, total;
@@ -509,7 +681,7 @@ static BwdPlan plan_backward(const gnode_batch* b) {
     const int hw_per_block = ROW_THREADS / 16;
     p.grid_row = (int)std::min<int64_t>((b->M + hw_per_block - 1) / hw_per_block, (int64_t)b->sm_count * 8);
     p.grid_tile1 = std::min(b->n_tiles, 2 * b->sm_count);
-    p.grid_tile3 = std::min(b->n_tiles, b->sm_count);
+    p.grid_tile3 = std::min(b->n_tiles, (vjp_kernel_choice() == 2 ? 2 : 1) * b->sm_count);
     size_t o = 0;
     p.off_a = o;  o += align_up(3 * M * H * sizeof(float), 256);
     p.off_sp = o; o += align_up(M * H * sizeof(float), 256);
@@ -551,6 +723,7 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
     if (!configured[b->device & 63]) {
         GN_CUDA(cudaFuncSetAttribute(bwd_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SM_TOTAL));
         GN_CUDA(cudaFuncSetAttribute(bwd_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SM_TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(bwd_vjp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3B_SM_TOTAL));
         configured[b->device & 63] = true;
     }
     const size_t M = (size_t)b->M;
@@ -588,7 +761,8 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
         bwd_gz_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
         a.part = plin;
-        bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
+        if (vjp_kernel_choice() == 2) bwd_vjp2_kernel<<<pl.grid_tile3, K3B_THREADS, K3B_SM_TOTAL, stream>>>(a);
+        else bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
         GN_LAUNCH_CHECK();
         return GNODE_OK;
     };
