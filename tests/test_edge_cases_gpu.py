@@ -83,3 +83,28 @@ def test_bench_graph_kernel_structures_agree(gn):
         print("%s vs fp32 FFMA kernel on the bench graph: %.3e" % (name, err))
         assert err < 5e-6, (name, err)
     assert (out["dual"].sum(-1) - 1).abs().max().item() < 1e-6
+
+
+def test_bench_size_batch_against_oracle(gn):
+    """BASELINE.json's bench configuration at full graph size (epinions stand-in, BA N=75,879) and a batch large enough
+    for the one-launch-per-step regime with the dynamic tile scheduler (16 trials = 1.2M rows): one trial of the batch
+    against the CPU oracle (bar 1e-5), the same trial rolled out alone (persistent single-launch regime) bitwise equal
+    to its rows inside the batch, probabilities normalised and finite everywhere."""
+    from gn_ode_sir_b200 import synth
+    A = synth.epinions_standin(0)
+    N, B, probe = A.shape[0], 16, 11
+    params = orc.default_params(64, seed=0)
+    xs = [orc.synthetic_trial(N, 64, b) for b in range(B)]          # the bench recipe (RandomState(1000 + b))
+    t = orc.time_grid(20, 0.5)
+    graph = gn.DeviceGraph(A)
+    dt = gn.rollout.dt_array(t)
+    with torch.no_grad():
+        full = gn.rollout.rollout(torch.cat(xs).to(DEV), gn.DeviceBatch([graph] * B), dt, dev_params(params))
+        alone = gn.rollout.rollout(xs[probe].to(DEV), gn.DeviceBatch([graph]), dt, dev_params(params))
+    mine = full[:, probe * N:(probe + 1) * N]
+    assert torch.equal(alone, mine)
+    assert torch.isfinite(full).all() and (full.sum(-1) - 1).abs().max().item() < 1e-6
+    want = orc.forward(xs[probe], params, orc.batch_coo([A], [0]), t)
+    err = (mine.cpu() - want).abs().max().item()
+    print("bench-size trial vs CPU oracle: %.3e" % err)
+    assert err < 1e-5, err

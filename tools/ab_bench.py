@@ -14,12 +14,23 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--trials", type=int, default=64)
 ap.add_argument("--rounds", type=int, default=3)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--heavy", action="store_true", help="add 8 hubs of degree ~3000 (max degree like soc-Epinions1)")
 ap.add_argument("configs", nargs="+")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
 L = _lib.lib()
 A = synth.epinions_standin(0)
+if args.heavy:
+    import scipy.sparse
+    rng = np.random.RandomState(1)
+    rows, cols = [], []
+    for h in range(8):
+        nb = rng.choice(A.shape[0], 3000, replace=False)
+        nb = nb[nb != h]
+        rows += [np.full(len(nb), h), nb]; cols += [nb, np.full(len(nb), h)]
+    Bm = scipy.sparse.csr_matrix((np.ones(sum(len(r) for r in rows), dtype=np.int8), (np.concatenate(rows), np.concatenate(cols))), shape=A.shape)
+    A = (A + Bm).tocsr(); A.sum_duplicates(); A.data[:] = 1; A.sort_indices()
 N, B, T = A.shape[0], args.trials, 40
 torch.manual_seed(0)
 of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, dev)
