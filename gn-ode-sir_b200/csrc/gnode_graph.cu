@@ -1,5 +1,6 @@
 // Graph / batch handles and the standalone neighbour aggregation (a6, a7).
 #include <algorithm>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 
@@ -163,6 +164,7 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
     b->n_tiles = (int32_t)((M + TILE - 1) / TILE);
     std::vector<int32_t> tile_inst(b->n_tiles);
     std::vector<int64_t> tile_cost(b->n_tiles, 0);
+    std::vector<int32_t> tile_maxdeg(b->n_tiles, 0);
     int32_t cur = 0;
     for (int32_t t = 0; t < b->n_tiles; ++t) {
         const int64_t r = (int64_t)t * TILE;
@@ -175,6 +177,7 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
             const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
             const int64_t nloc = g - inst[ii].row0;
             tile_cost[t] += rp[nloc + 1] - rp[nloc];
+            tile_maxdeg[t] = std::max(tile_maxdeg[t], rp[nloc + 1] - rp[nloc]);
         }
     }
     // Processing order for the dynamic tile scheduler: instance by instance (= trial by trial, so that concurrently
@@ -201,6 +204,33 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
     }
     GN_CUDA(cudaGetDevice(&b->device));
     GN_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
+    // Tail control. A row is summed by ONE half-warp in rounds of 8 neighbours, strictly in ascending column order (the
+    // order of the reference's CPU scatter_add_: hub sums of ~1e3 amplify any re-association to ~1e-3 in the hidden
+    // state, so the row is not split across warps). A round costs ~2.4k cycles under load, i.e. a tile with a hub row of
+    // degree d occupies its pipeline for about d / 128 ordinary tile times (measured: 0.65 ms for two 4k-degree rows),
+    // whatever the other rows do. Such a tile must not START late: the hub tile of the last trials would otherwise run
+    // on alone after every other pipeline has drained (measured: +0.6 ms per launch, -14 % at 64 trials with 3k-degree
+    // hubs). Tiles whose estimated end passes the end of the launch are hoisted to the very front of the order (longest
+    // first); all others keep the trial-by-trial order above.
+    if (getenv("GNODE_NO_TAIL_HOIST") == nullptr) {
+        const int64_t n = (int64_t)order.size();
+        const int64_t P = 2 * (int64_t)std::max(1, b->sm_count);          // tile pipelines in flight
+        std::vector<char> hoist(b->n_tiles, 0);
+        std::vector<int32_t> front;
+        for (int64_t q = 0; q < n; ++q) {
+            const int32_t t = order[q];
+            if (tile_maxdeg[t] < 256) continue;
+            const int64_t len = tile_maxdeg[t] / 128 + 1;                  // in ordinary tile times
+            if (q > n - P * (len + 1)) { hoist[t] = 1; front.push_back(t); }
+        }
+        if (!front.empty() && (int64_t)front.size() < n) {
+            std::stable_sort(front.begin(), front.end(), [&](int32_t x, int32_t y) { return tile_maxdeg[x] > tile_maxdeg[y]; });
+            std::vector<int32_t> reordered(front);
+            reordered.reserve(order.size());
+            for (int32_t t : order) if (!hoist[t]) reordered.push_back(t);
+            order.swap(reordered);
+        }
+    }
     GN_CUDA(cudaMalloc(&b->d_inst, sizeof(GnInstance) * n_inst));
     GN_CUDA(cudaMalloc(&b->d_tile_inst, sizeof(int32_t) * b->n_tiles));
     GN_CUDA(cudaMalloc(&b->d_tile_order, sizeof(int32_t) * b->n_tiles));
