@@ -38,6 +38,7 @@ R_STATE_NOTE = {
        "neither read nor written, i.e. 512 of the 2060 algorithmic bytes per node-step are not moved -- the roofline denominator "
        "stays 2060 B (SURVEY 8d); GNODE_R_STATE=full keeps the plane",
     0: "full 64-float R plane (GNODE_R_STATE=full)"}
+JSON_OUT = sys.stdout
 UNIT = "node-steps/s"
 METRIC = "GN-ODE rollout node-steps/s (epinions)"
 
@@ -178,7 +179,7 @@ def run_reference_arm(args, rank, world):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=JSON_OUT, flush=True)
 
 
 def workload_config(args, world, r_state=None):
@@ -192,6 +193,12 @@ def workload_config(args, world, r_state=None):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that libraries write to file descriptor 1 (NCCL prints its
+    # version banner there under torchrun) is sent to stderr, and the JSON line goes to the saved descriptor.
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -353,7 +360,7 @@ def main():
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, int(L.gnode_get_r_state())),
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=JSON_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
