@@ -75,7 +75,7 @@ struct gnode_batch {
     int32_t* d_tile_inst = nullptr;  // [n_tiles] instance that owns the first row of each tile
     int32_t* d_tile_order = nullptr; // [n_tiles] processing order: hub-heavy tiles first, then row-major
     int2* d_sched = nullptr;         // [n_tiles] by sequence number: {tile, first row of the look-ahead I' prefetch or -1}
-    int4* d_tile_meta = nullptr;     // [n_tiles] {first CSR entry, entry count, owning instance, 1 if inside one instance}
+    int4* d_tile_meta = nullptr;     // [n_tiles] {first CSR entry, entry count, owning instance, bit 0: inside one instance, bit 1: hub relay}
     int4* d_sub_meta = nullptr;      // [2 n_tiles] the same for the two 64-row halves of every tile
     int device = 0;
     int sm_count = 0;

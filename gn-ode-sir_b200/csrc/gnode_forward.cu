@@ -799,6 +799,7 @@ struct PipeCfg {
     static constexpr int RSTEP = PT / 16;                  // rows per pass (32 / 16)
     static constexpr int PASS = RSTEP * 128;               // byte offset between the passes' rows in an operand tile
     static constexpr int CAP = 3 * PT;                     // colidx entries staged per tile (3 per thread)
+    static constexpr int HUB_DEG = 512;                    // longer rows: loads by the whole pipeline, adds relayed in order
     static constexpr int KBLK = TR * 128;                  // bytes of one K-block (32 fp32) of the A operand
     static constexpr int P_X = 0;                          // A operand hi / parked neighbour sums
     static constexpr int P_L = 2 * KBLK;                   // A operand lo / S' / I' staging
@@ -814,6 +815,7 @@ struct PipeCfg {
     static constexpr int TMEM_COLS = 128 * NP;             // one [TR x 80] accumulator per pipeline, 128 columns apart
     static_assert(TOTAL + 1024 <= 200704, "stay inside the 196 KB shared-memory carve-out (60 KB of L1 left)");
     static_assert(PT / 4 >= TR, "beta / gamma staging needs a quarter of the pipeline's threads per array");
+    static_assert((TR + 2 + TR / 32) * 4 <= TR * 4 + 32, "hub mask lives in the pad behind the rowptr slice");
     // byte offset of the 16-byte chunk c4 of tile row r (canonical UMMA K-major SWIZZLE_128B, two K-blocks)
     static __device__ __forceinline__ int sw(int r, int c4) { return (c4 >> 3) * KBLK + (r << 7) + (((c4 & 7) ^ (r & 7)) << 4); }
 };
@@ -854,6 +856,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     float* hs_s = reinterpret_cast<float*>(hb + C::P_HS);
     float* hr_s = reinterpret_cast<float*>(hb + C::P_HR);
     int* ci_s = reinterpret_cast<int*>(hb + C::P_CI);
+    unsigned* hub_mask = reinterpret_cast<unsigned*>(rp_s + TR + 2);   // TR / 32 words in the pad behind the rowptr slice
     const int bar_id = 1 + half;
 #define HSYNC() umma::bar_sync(bar_id, PT)
 
@@ -959,7 +962,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         const DTileMeta m = *meta;                                    // written before the last barrier passed
         if (m.seq >= n_tiles) break;
         const int tile0 = m.tile0, nrows = m.nrows, i_row0 = m.i_row0, ebase = m.ebase;
-        const bool single = m.single != 0;
+        const bool single = (m.single & 1) != 0;
+        const bool relay = (m.single & 2) != 0 && !(a.dbg & 4194304);   // the tile has isolated hub rows (host cost model)
 
         // ---- P1: operand tiles for GEMM1 (S_k rows); the tile's CSR slice, beta/gamma -> smem
         //      (every address is known from the metadata: all these loads are in flight together)
@@ -984,6 +988,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             }
             umma::fence_proxy_async();
             if (t == 0) *row_ctr = 0;
+            if (t < TR / 32) hub_mask[t] = 0u;
             if (single && t <= nrows) rp_s[t] = rpv;
             if (single) {
 #pragma unroll
@@ -997,6 +1002,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         const bool do_g1 = !(a.dbg & 16), do_g2 = !(a.dbg & 8);       // timing experiments only
         if (do_g1 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        // rows longer than HUB_DEG are summed by the whole pipeline in P3a (in-order relay): mark them while the GEMM runs
+        if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
         if (do_g1) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }        // hardware-suspended wait (no spinning)
         umma::fence_after_sync();
         if (do_g1) {
@@ -1045,6 +1052,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     const int rr = 2 * p + (lane >> 4);
                     int e_rel = 0, deg = 0;
                     if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
+                    if (relay && deg > C::HUB_DEG) deg = 0;                    // hub row: in-order relay below
                     const int over = (e_rel + deg > C::CAP) ? 1 : 0;
                     float4 acc;
                     if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
@@ -1053,6 +1061,71 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                         acc = gather_smem_z(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
                     sts4(Xs, C::sw(rr, l), acc);
                     p = static_rows ? pn : __shfl_sync(0xffffffffu, pn, 0);
+                }
+                // Hub rows (power-law graphs: degrees in the thousands). One half-warp walking the row in rounds of 8 pays a
+                // full memory round trip per round (~2.4k cycles under load: 0.5 ms for a 3k-degree row) while the rest of
+                // the pipeline waits at the barrier. The sum must stay strictly sequential in ascending column order (the
+                // order of the reference's CPU scatter_add_; a hub's ~1e3 sum amplifies any re-association to ~1e-3 in its
+                // hidden state), but only the ADDS are serial: every half-warp of the pipeline LOADS 8 consecutive
+                // neighbour rows of a 256-neighbour super-round at once, and the running sum is relayed through shared
+                // memory from warp to warp in column order (lower half-warp, shuffle, upper half-warp, next warp). Bitwise
+                // the same result as the serial walk, one memory round trip per 256 neighbours instead of per 8.
+                // Several hub rows in ONE tile are walked concurrently by different warps in the serial scheme, while the relay
+                // takes them one after the other (~7k cycles per super-round, mostly hand-offs): gnode_batch_create sets the
+                // relay flag of a tile only where its cost model favours it (isolated hubs: 6-10x shorter tile).
+                if (relay) {
+                    HSYNC();                                             // every ordinary row is parked; the colidx slice is dead
+                    volatile float* run = reinterpret_cast<volatile float*>(ci_s);          // [64] running sum
+                    uint64_t* hbar = reinterpret_cast<uint64_t*>(ci_s + H);                  // one mbarrier per warp: "your turn"
+                    if (t < PT / 32) umma::mbar_init(&hbar[t], 1);
+                    HSYNC();
+                    constexpr int SR = (PT / 16) * 8;                    // neighbours per super-round
+                    int nsr_done = 0;                                    // super-rounds so far (phase bookkeeping)
+#pragma unroll 1
+                    for (int w = 0; w < TR / 32; ++w) {
+                        unsigned mm = hub_mask[w];
+                        while (mm) {
+                            const int r = 32 * w + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const int dg = rp_s[r + 1] - rp_s[r];
+                            const int* cp = m.colidx + rp_s[r];
+                            const int n_sr = (dg + SR - 1) / SR;
+#pragma unroll 1
+                            for (int sr = 0; sr < n_sr; ++sr) {
+                                const int j0 = sr * SR + hw * 8;
+                                float4 v[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int c = (j0 + k < dg) ? cp[j0 + k] : zrow;
+                                    v[k] = ldg4_hint(lane_base + (size_t)(unsigned)c * H, pol_keep);
+                                }
+                                // warp w > 0 is released by warp w - 1 of this super-round, warp 0 by the last warp of the previous one
+                                if (warp > 0) umma::mbar_wait(&hbar[warp], (uint32_t)(nsr_done & 1));
+                                else if (nsr_done > 0) umma::mbar_wait(&hbar[0], (uint32_t)((nsr_done - 1) & 1));
+                                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (!(sr == 0 && warp == 0)) {
+                                    sum.x = run[4 * l + 0]; sum.y = run[4 * l + 1]; sum.z = run[4 * l + 2]; sum.w = run[4 * l + 3];
+                                }
+                                if (lane < 16) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                }
+                                sum.x = __shfl_sync(0xffffffffu, sum.x, l); sum.y = __shfl_sync(0xffffffffu, sum.y, l);
+                                sum.z = __shfl_sync(0xffffffffu, sum.z, l); sum.w = __shfl_sync(0xffffffffu, sum.w, l);
+                                if (lane >= 16) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                    run[4 * l + 0] = sum.x; run[4 * l + 1] = sum.y; run[4 * l + 2] = sum.z; run[4 * l + 3] = sum.w;
+                                    if (sr == n_sr - 1 && warp == PT / 32 - 1) sts4(Xs, C::sw(r, l), sum);
+                                }
+                                __syncwarp();
+                                if (lane == 0) umma::mbar_arrive(&hbar[(warp + 1) & (PT / 32 - 1)]);   // release: orders the stores above
+                                ++nsr_done;
+                            }
+                        }
+                    }
+                    HSYNC();
+                    if (t < PT / 32) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(&hbar[t])) : "memory");
                 }
             } else {                                         // tile spans several (small) instances
                 int inst = m.inst0;

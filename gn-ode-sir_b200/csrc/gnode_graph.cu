@@ -263,6 +263,18 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
                     const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
                     tm[u].x = rp[r0 - inst[ii].row0];
                     tm[u].y = rp[r1 - inst[ii].row0] - tm[u].x;
+                    // bit 1: sum the tile's hub rows (degree > 512) by the in-order relay of the pipelined step kernel.
+                    // Cost model (cycles, measured): relay = 7k per super-round of 2 * rows neighbours, hub after hub;
+                    // serial = ~2k per round of 8, hub rows on different warps side by side -> longest row decides.
+                    // The relay is chosen only where it wins by 2x (isolated hubs), e.g. not for the first tile of a
+                    // Barabasi-Albert graph, whose rows are all hubs.
+                    int64_t super_rounds = 0, maxdeg = 0;
+                    for (int64_t g = r0; g < r1; ++g) {
+                        const int64_t d = rp[g - inst[ii].row0 + 1] - rp[g - inst[ii].row0];
+                        maxdeg = std::max(maxdeg, d);
+                        if (d > 512) super_rounds += (d + 2 * rows - 1) / (2 * rows);
+                    }
+                    if (super_rounds > 0 && 2 * 7000 * super_rounds < 2000 * (maxdeg / 8)) tm[u].w |= 2;
                 }
             }
         };

@@ -108,3 +108,39 @@ def test_bench_size_batch_against_oracle(gn):
     err = (mine.cpu() - want).abs().max().item()
     print("bench-size trial vs CPU oracle: %.3e" % err)
     assert err < 1e-5, err
+
+
+def test_hub_relay_is_bitwise_the_serial_walk(gn, monkeypatch):
+    """Rows longer than 512 neighbours are loaded by the whole tile pipeline and added by an in-order relay; the
+    result must be BITWISE the serial ascending-column walk (GNODE_DBG bit 22 switches the relay off), for isolated
+    hubs in different tiles, several hubs in one tile, a hub at degree 513 (just above the threshold) and one at 512
+    (just below), with batches in the persistent and in the launch-per-step regime."""
+    import networkx as nx
+    rng = np.random.RandomState(3)
+    N = 6000
+    A = scipy.sparse.lil_matrix(scipy.sparse.csr_matrix(nx.adjacency_matrix(nx.barabasi_albert_graph(N, 4, seed=2))))
+    for hub, deg in ((5, 2500), (6, 1300), (700, 513), (701, 512), (3333, 900), (5999, 777)):
+        nb = rng.choice(N, deg, replace=False)
+        nb = nb[nb != hub]
+        A[hub, nb] = 1
+        A[nb, hub] = 1
+    A = scipy.sparse.csr_matrix(A)
+    A.data[:] = 1
+    A.sort_indices()
+    deg = np.diff(A.indptr)
+    assert (deg > 512).sum() >= 5 and deg.max() > 2400
+    params = dev_params(orc.default_params(64, seed=4))
+    graph = gn.DeviceGraph(A)
+    dt = gn.rollout.dt_array(orc.time_grid(20, 0.5))
+    for B in (2, 120):                         # 94 tiles (persistent rollout) / 5625 tiles (one launch per step)
+        x = torch.cat([orc.synthetic_trial(N, 64, 40 + b) for b in range(B)]).to(DEV)
+        batch = gn.DeviceBatch([graph] * B)
+        monkeypatch.delenv("GNODE_DBG", raising=False)
+        with torch.no_grad():
+            relay = gn.rollout.rollout(x, batch, dt, params)
+        monkeypatch.setenv("GNODE_DBG", str(1 << 22))
+        with torch.no_grad():
+            serial = gn.rollout.rollout(x, batch, dt, params)
+        monkeypatch.delenv("GNODE_DBG", raising=False)
+        assert torch.equal(relay, serial), (B, (relay - serial).abs().max().item())
+        assert torch.isfinite(relay).all()

@@ -15,6 +15,7 @@ ap.add_argument("--trials", type=int, default=64)
 ap.add_argument("--rounds", type=int, default=3)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--heavy", action="store_true", help="add 8 hubs of degree ~3000 (max degree like soc-Epinions1)")
+ap.add_argument("--spread", action="store_true", help="with --heavy: the 8 hubs sit in 8 different tiles (isolated hubs, as in real graphs)")
 ap.add_argument("configs", nargs="+")
 args = ap.parse_args()
 
@@ -26,6 +27,8 @@ if args.heavy:
     rng = np.random.RandomState(1)
     rows, cols = [], []
     for h in range(8):
+        if args.spread:
+            h = 77 + 128 * 70 * h
         nb = rng.choice(A.shape[0], 3000, replace=False)
         nb = nb[nb != h]
         rows += [np.full(len(nb), h), nb]; cols += [nb, np.full(len(nb), h)]
