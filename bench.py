@@ -301,6 +301,7 @@ def main():
     bc = max(1, min(args.e2e_chunk, args.trials))
     n_chunks = (args.trials + bc - 1) // bc
     x_pin = x_host.pin_memory()
+    del x_host                                   # one host copy per rank (8 ranks share the box's RAM)
     out_pin = torch.empty((n_chunks, T, bc * N, 3), dtype=torch.float32).pin_memory()   # chunk-major host result
     h2d_bytes = x_pin.numel() * 4
     d2h_bytes = T * rows * 3 * 4
