@@ -62,7 +62,9 @@ def l1_on_rollout(model, criterion, x, y, maxTime, deltaT):
 def run_epoch(model, optimizer, criterion, device, train_batches, val_batches, maxTime, deltaT):
     """One epoch of Adam steps followed by a validation sweep; returns item-weighted mean losses."""
     model.train()
-    tot, items, fwd_time = 0.0, 0, 0.0
+    # the item-weighted loss sums stay on the device: one host read per epoch instead of one per batch (the
+    # reference's loss.item() per batch, ode_nn_ngraph_sim.py:247, drains the stream between optimiser steps)
+    tot, items, fwd_time = torch.zeros((), dtype=torch.float64, device=device), 0, 0.0
     for x, y in train_batches:
         x, y = x.to(device), y.to(device)
         optimizer.zero_grad()
@@ -71,17 +73,17 @@ def run_epoch(model, optimizer, criterion, device, train_batches, val_batches, m
         fwd_time += time.time() - t0
         loss.backward()
         optimizer.step()
-        tot += loss.item() * n
+        tot += loss.detach().double() * n
         items += n
     model.eval()
-    vtot, vitems = 0.0, 0
+    vtot, vitems = torch.zeros((), dtype=torch.float64, device=device), 0
     with torch.no_grad():
         for x, y in val_batches:
             loss, n = l1_on_rollout(model, criterion, x.to(device), y.to(device), maxTime, deltaT)
-            vtot += loss.item() * n
+            vtot += loss.double() * n
             vitems += n
     print("Time: ", fwd_time)
-    return tot / max(items, 1), vtot / max(vitems, 1)
+    return float(tot.item()) / max(items, 1), float(vtot.item()) / max(vitems, 1)
 
 
 def evaluate(model, criterion, device, batches, maxTime, deltaT):
