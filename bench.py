@@ -225,6 +225,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the GN-ODE rollout has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
+    if world > 1:
+        # one process per GPU: host buffers next to the GPU (8 ranks x 28 GB/s of PCIe traffic must not cross sockets)
+        from gn_ode_sir_b200.parallel import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
+        print("bench.py: rank %d bound to %s" % (rank, ("%d CPUs near GPU %d" % (len(numa_cpus), local_rank)) if numa_cpus else "no CPU set (unchanged)"),
+              file=sys.stderr, flush=True)
     dist = None
     if world > 1:
         import torch.distributed as dist_

@@ -5,9 +5,48 @@ ranks with the graph(s) and the ~19 KB of weights replicated. Inference needs no
 needs ONE all-reduce (sum) of the flattened parameter gradient per optimiser step -- latency-bound at
 4.8k floats, so it is issued as a single flat buffer. One process per GPU (torch.distributed, NCCL on
 GPUs / gloo in the CPU tests)."""
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+def bind_to_gpu_numa_node(device_index, min_cpus=2):
+    """Pin the calling process to the CPUs next to its GPU (NVML's ideal CPU affinity, intersected with the CPUs this
+    process may use), BEFORE it allocates pinned host buffers: the pages then come from the GPU's own NUMA node. With one
+    process per GPU and every rank streaming inputs and results over PCIe, buffers that land on the other socket cap
+    the aggregate host traffic (8 ranks: 120 GB/s measured). Returns the CPU list, or None when nothing was changed
+    (no NVML, fewer than `min_cpus` usable CPUs, already bound, or GNODE_NO_NUMA_BIND set)."""
+    if os.environ.get("GNODE_NO_NUMA_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            props = torch.cuda.get_device_properties(device_index)
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            for arg in (bus, bus.encode()):
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByPciBusId(arg)
+                    break
+                except (TypeError, AttributeError):
+                    continue
+        except Exception:
+            handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, 16)            # 1024 CPU bits
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = ideal & allowed
+        if len(target) < min_cpus or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        return sorted(target)
+    except Exception:
+        return None
 
 
 def shard_instances(sizes, world_size):

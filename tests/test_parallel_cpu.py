@@ -82,3 +82,19 @@ def test_allreduce_is_noop_without_process_group():
     g = m.weight.grad.clone()
     parallel.allreduce_gradients(m.parameters())
     assert torch.equal(g, m.weight.grad)
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    """bind_to_gpu_numa_node never raises and leaves the affinity alone when NVML / the device is not there."""
+    import os
+    from gn_ode_sir_b200 import parallel
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert parallel.bind_to_gpu_numa_node(0) is None
+        assert os.sched_getaffinity(0) == before
+    os.environ["GNODE_NO_NUMA_BIND"] = "1"
+    try:
+        assert parallel.bind_to_gpu_numa_node(0) is None
+    finally:
+        del os.environ["GNODE_NO_NUMA_BIND"]
+    assert os.sched_getaffinity(0) == before
