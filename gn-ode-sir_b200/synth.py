@@ -87,3 +87,17 @@ def barabasi_albert_csr_fast(n, m, seed=0, chunk=4096):
 def ba_stress(seed=0):
     """BA(N=2,000,000, m=10): ~20M undirected edges, mean degree ~20 (BASELINE.json configs[4])."""
     return barabasi_albert_csr_fast(2_000_000, 10, seed)
+
+
+def synthetic_trial(n_nodes, H, trial_id, n_seeds=2):
+    """One [N, 3+H] input block in the layout main() of the reference builds (ode_nn_ngraph_sim.py:371-390): columns
+    S0 | I0 | R0 | beta gamma 0...; seeds and rates drawn like monitorer-sim.py:116-119 from RandomState(1000 + id)."""
+    import torch
+    rng = np.random.RandomState(1000 + trial_id)
+    seeds = rng.choice(n_nodes, n_seeds, replace=False)
+    beta, gamma = rng.uniform(0.1, 0.5), rng.uniform(0.1, 0.5)
+    x = torch.zeros(n_nodes, 3 + H, dtype=torch.float32)
+    x[seeds, 1] = 1.0
+    x[:, 0] = 1.0 - x[:, 1]
+    x[:, 3], x[:, 4] = beta, gamma
+    return x

@@ -5,13 +5,12 @@ os.environ["GNODE_DBG"] = str(int(os.environ.get("GNODE_DBG", "0")) | 128)
 import numpy as np, torch
 import gn_ode_sir_b200 as gn
 from gn_ode_sir_b200 import _lib, synth
-from oracle import gnode_oracle as orc
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 A = synth.epinions_standin(0); N = A.shape[0]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, dev); blk = gn.ode_sim.ODEBlock(20, 0.5, N, [0, 1], 64, of, dev).to(dev).eval()
-x = torch.stack([orc.synthetic_trial(N, 64, b) for b in range(trials)]).to(dev)
+x = torch.stack([synth.synthetic_trial(N, 64, b) for b in range(trials)]).to(dev)
 L = _lib.lib()
 with torch.no_grad():
     blk(x); torch.cuda.synchronize()

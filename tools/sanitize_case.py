@@ -5,7 +5,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gn_ode_sir_b200 as gn
 from gn_ode_sir_b200 import synth
-from oracle import gnode_oracle as orc
 dev = torch.device("cuda:0")
 import numpy as np, scipy.sparse
 A = scipy.sparse.lil_matrix(synth.barabasi_albert_csr(1500, 3, 0)); N = A.shape[0]; B = 3
@@ -14,7 +13,7 @@ A[900, nb] = 1; A[nb, 900] = 1                       # isolated hub (degree > 51
 A = scipy.sparse.csr_matrix(A); A.data[:] = 1; A.sort_indices()
 torch.manual_seed(0)
 of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, dev); blk = gn.ode_sim.ODEBlock(4, 0.5, N, [0, 1], 64, of, dev).to(dev)
-x = torch.stack([orc.synthetic_trial(N, 64, b) for b in range(B)]).to(dev)
+x = torch.stack([synth.synthetic_trial(N, 64, b) for b in range(B)]).to(dev)
 with torch.no_grad():
     S, I, R = blk(x)
 S, I, R = blk(x)

@@ -4,13 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import gn_ode_sir_b200 as gn
 from gn_ode_sir_b200 import synth
-from oracle import gnode_oracle as orc
 dev = torch.device("cuda:0")
 for name, n, m, B in (("karate-size", 34, 2, 1), ("fb-social-size", 1893, 7, 8), ("fb-social-size", 1893, 7, 64), ("epinions-size", 75879, 5, 4)):
     A = synth.barabasi_albert_csr(n, m, 0); N = A.shape[0]
     torch.manual_seed(0)
     of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, dev); blk = gn.ode_sim.ODEBlock(20, 0.5, N, [0, 1], 64, of, dev).to(dev)
-    x = torch.stack([orc.synthetic_trial(N, 64, b) for b in range(B)]).to(dev)
+    x = torch.stack([synth.synthetic_trial(N, 64, b) for b in range(B)]).to(dev)
     w = torch.randn(40, B * N, 3, device=dev)
     def step():
         blk.zero_grad()
