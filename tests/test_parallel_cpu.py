@@ -98,3 +98,11 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
     finally:
         del os.environ["GNODE_NO_NUMA_BIND"]
     assert os.sched_getaffinity(0) == before
+
+
+def test_package_input_recipe_matches_oracle():
+    """The package's synthetic (beta, gamma, seed-set) input recipe (bench tools) is the oracle's, bit for bit."""
+    from gn_ode_sir_b200 import synth
+    from oracle import gnode_oracle as orc
+    for n, tid in ((34, 0), (620, 7), (1893, 1234)):
+        assert torch.equal(synth.synthetic_trial(n, 64, tid), orc.synthetic_trial(n, 64, tid))
