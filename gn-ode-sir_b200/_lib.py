@@ -14,6 +14,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
 GNODE_H = 64
+GNODE_TRIAL_LDX = 8            # row stride of the compact x written by gnode_rollout_forward_trials
 GRAD_ADJOINT, GRAD_DISCRETE = 0, 1
 GRAD_LAYOUT = (("odefunc.linear.weight", (GNODE_H, GNODE_H)), ("odefunc.linear.bias", (GNODE_H,)),
                ("linearS1.weight", (GNODE_H, 1)), ("linearS1.bias", (GNODE_H,)),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "gnode_get_step_kernel": (c_int, []),
     "gnode_set_r_state": (c_int, [c_int]),
     "gnode_get_r_state": (c_int, []),
+    "gnode_set_persistent": (c_int, [c_int]),
+    "gnode_get_persistent": (c_int, []),
     "gnode_debug_phase_cycles": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "gnode_graph_create": (c_int, [c_int32, c_int64, c_int32_p, c_int32_p, ctypes.POINTER(c_void_p)]),
     "gnode_graph_destroy": (c_int, [c_void_p]),
@@ -50,10 +53,23 @@ SIGNATURES = {
     "gnode_rollout_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "gnode_rollout_forward": (c_int, [c_void_p, c_void_p, c_int64, ctypes.POINTER(GnodeParams), c_int32,
                                       c_float_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnode_rollout_forward_sel": (c_int, [c_void_p, c_void_p, c_int64, ctypes.POINTER(GnodeParams), c_int32,
+                                          c_float_p, c_int32_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnode_expand_trials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gnode_rollout_trials_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "gnode_rollout_forward_trials": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             ctypes.POINTER(GnodeParams), c_int32, c_float_p, c_int32_p, c_int32,
+                                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnode_backward_workspace_bytes": (c_size_t, [c_void_p]),
     "gnode_rollout_backward": (c_int, [c_void_p, c_void_p, c_int64, ctypes.POINTER(GnodeParams), c_int32,
                                        c_float_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t,
                                        c_void_p]),
+    "gnode_rollout_backward_sel": (c_int, [c_void_p, c_void_p, c_int64, ctypes.POINTER(GnodeParams), c_int32,
+                                           c_float_p, c_void_p, c_void_p, c_int32_p, c_int32, c_int32, c_void_p,
+                                           c_void_p, c_size_t, c_void_p]),
+    "gnode_l1_scratch_bytes": (c_size_t, []),
+    "gnode_l1_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, ctypes.c_float, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
 }
 
 _lib = None

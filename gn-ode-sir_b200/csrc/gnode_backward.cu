@@ -708,11 +708,23 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
                                       int32_t T, const float* dt_host, const float* traj, const float* grad_probs,
                                       int32_t grad_mode, float* grads_out, void* workspace, size_t workspace_bytes,
                                       void* stream_) {
+    return gnode_rollout_backward_sel(b, x, ldx, p, T, dt_host, traj, grad_probs, nullptr, 0, grad_mode, grads_out,
+                                      workspace, workspace_bytes, stream_);
+}
+
+extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                          int32_t T, const float* dt_host, const float* traj, const float* grad_probs,
+                                          const int32_t* out_steps, int32_t n_out, int32_t grad_mode, float* grads_out,
+                                          void* workspace, size_t workspace_bytes, void* stream_) {
     if (!b || !x || !p || !traj || !grad_probs || !grads_out || !workspace || T < 1 || ldx < 5 ||
         (T > 1 && !dt_host) || (grad_mode != GNODE_GRAD_ADJOINT && grad_mode != GNODE_GRAD_DISCRETE)) {
         set_error("gnode_rollout_backward: bad arguments (T=%d ldx=%lld grad_mode=%d)", T, (long long)ldx, grad_mode);
         return GNODE_ERR_ARG;
     }
+    OutSel sel;
+    int rc = make_out_sel(T, out_steps, n_out, &sel, "gnode_rollout_backward_sel");
+    if (rc) return rc;
+    if ((rc = check_current_device(b, "gnode_rollout_backward"))) return rc;
     const BwdPlan pl = plan_backward(b);
     if (workspace_bytes < pl.total) {
         set_error("gnode_rollout_backward: workspace too small (%zu < %zu)", workspace_bytes, pl.total);
@@ -742,8 +754,11 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
     GN_CUDA(cudaMemsetAsync(ws + pl.off_pdec, 0, pl.off_penc - pl.off_pdec, stream));
 
     auto state = [&](int j) { return traj + (size_t)j * 3 * M * H; };
-    auto gp = [&](int j) { return grad_probs + (size_t)j * M * 3; };
+    // cotangent of grid point j, or null when its probabilities were not emitted (sparse dL/dprobs: the loss of the
+    // reference consumes only the grid points int(i/deltaT), ode_nn.py:249-261)
+    auto gp = [&](int j) -> const float* { return sel.slot[j] >= 0 ? grad_probs + (size_t)sel.slot[j] * M * 3 : nullptr; };
     auto dec_only = [&](int j) -> int {
+        if (!gp(j)) return GNODE_OK;
         a.y = state(j); a.gP = gp(j); a.part = pdec; a.only_dec = 1; a.dt = 0.f;
         bwd_row_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
@@ -766,15 +781,17 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
         GN_LAUNCH_CHECK();
         return GNODE_OK;
     };
-    int rc;
+    int jmax = T - 1;                             // last grid point with a cotangent: the adjoint is zero beyond it
+    while (jmax > 0 && sel.slot[jmax] < 0) --jmax;
     if (grad_mode == GNODE_GRAD_ADJOINT) {
-        for (int j = T - 1; j >= 1; --j)
+        for (int j = jmax; j >= 1; --j)
             if ((rc = vjp_step(j, dt_host[j - 1], true))) return rc;
         if ((rc = dec_only(0))) return rc;
     } else {
         if ((rc = dec_only(T - 1))) return rc;
         for (int j = T - 2; j >= 0; --j) {       // D(y_j) must not enter the cotangent of the VJP at y_j
-            if ((rc = vjp_step(j, dt_host[j], false))) return rc;
+            // (the adjoint of y_{j+1} is still zero beyond the last grid point with a cotangent: no VJP to take there)
+            if (j + 1 <= jmax && (rc = vjp_step(j, dt_host[j], false))) return rc;
             if ((rc = dec_only(j))) return rc;
         }
     }

@@ -42,6 +42,19 @@ extern int64_t g_launches;
 
 }  // namespace gnode
 
+struct gnode_batch;
+namespace gnode {
+// Host-side description of which grid points are emitted: slot[k] = row block of `probs` for grid point k, or -1.
+struct OutSel {
+    std::vector<int> slot;
+    int n_out = 0, start = 0, stride = 1;
+    bool arithmetic = true;
+};
+int make_out_sel(int T, const int32_t* out_steps, int32_t n_out, OutSel* o, const char* what);
+// GNODE_ERR_ARG unless the handle's device is the calling thread's current device
+int check_current_device(const gnode_batch* b, const char* what);
+}  // namespace gnode
+
 // One graph: CSR pattern (and its transpose) resident in HBM.
 struct gnode_graph {
     int32_t n = 0;

@@ -58,11 +58,24 @@ struct StepArgs {
     float* st[2];
     float* ipb[2];        // I' ping-pong
     float* probs_base;    // [T][M][3]
-    const float* dt_dev;  // [T-1] device copy of the step sizes
+    const float* dt_dev;  // [T-1] device copy of the step sizes, or null: every step uses `dt`
+    const int* out_slot;  // [T] output slot of every grid point (-1: not emitted), or null: slot(k) = (k - out_start) / out_stride
+    int out_start, out_stride, n_out;   // arithmetic selection (identity: 0, 1, T)
     int* counters;        // one zeroed int per step (dynamic tile tickets)
     alignas(64) CUtensorMap tm_ip_out;   // [M rows][64] fp32 over ip_out, box 32 x 128, SWIZZLE_128B
     alignas(64) CUtensorMap tm_ipb[2];   // the same over ipb[0] / ipb[1] (persistent rollout)
+    // step_stream_kernel: the S_k tile arrives by TMA tensor loads (same box / swizzle = the UMMA operand layout)
+    alignas(64) CUtensorMap tm_s_in;     // [M rows][64] fp32 over the S plane of y_in (one launch per step)
+    alignas(64) CUtensorMap tm_sp[2];    // persistent rollout: over the S planes of st[0] / st[1], or [0] over the whole trajectory
 };
+
+// output slot of grid point k (-1: its probabilities are not emitted)
+__host__ __device__ __forceinline__ int out_slot_of(const StepArgs& a, int k) {
+    if (a.out_slot) return a.out_slot[k];
+    const int d = k - a.out_start;
+    if (d < 0 || d % a.out_stride != 0) return -1;
+    return d / a.out_stride < a.n_out ? d / a.out_stride : -1;
+}
 
 // shared-memory carve-up (bytes from a 1024-B aligned base; operand tiles need 1024-B alignment)
 constexpr int SM_X = 0;                        // 32 KB  operand tile (S_k, then I_{k+1})
@@ -946,8 +959,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             d.y_in = a.traj ? a.traj + (size_t)ks * plane3 : a.st[ks & 1];
             d.y_out = a.traj ? a.traj + (size_t)(ks + 1) * plane3 : a.st[(ks + 1) & 1];
             d.ip_in = a.ipb[ks & 1]; d.ip_out = a.ipb[(ks + 1) & 1];
-            d.probs = ks > 0 ? a.probs_base + (size_t)ks * M * 3 : nullptr;
-            d.dt = a.dt_dev[ks];
+            const int slot = out_slot_of(a, ks);
+            d.probs = (ks > 0 && slot >= 0) ? a.probs_base + (size_t)slot * M * 3 : nullptr;
+            d.dt = a.dt_dev ? a.dt_dev[ks] : a.dt;
             d.counter = a.counters ? a.counters + ks + 1 : nullptr;
             d.tm = &a.tm_ipb[(ks + 1) & 1];
         }
@@ -1319,6 +1333,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(*tslot, C::TMEM_COLS);
 }
+
+}  // namespace gnode
+#include "gnode_step_stream.cuh"
+namespace gnode {
 
 // Decoder + softmax of one stored state (the last grid point of the dual-kernel rollout): probs = softmax over
 // {S, I, R} of linearS2(relu(linear3(.)))  (ode_nn_ngraph_sim.py:170-188). Half-warp per row.
@@ -1760,11 +1778,32 @@ static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_
     return GNODE_OK;
 }
 
+template <bool FAST, bool RF>
+static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, false, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, true, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const int grid = std::min(b->n_tiles, b->sm_count);
+    if (a.n_steps > 0) {
+        void* params[] = {const_cast<StepArgs*>(&a)};
+        GN_CUDA(cudaLaunchCooperativeKernel((const void*)step_stream_kernel<FAST, true, RF>, dim3(grid), dim3(D_THREADS), params,
+                                            (size_t)StreamCfg::TOTAL, stream));
+        gnode::g_launches++;
+        return GNODE_OK;
+    }
+    step_stream_kernel<FAST, false, RF><<<grid, D_THREADS, StreamCfg::TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
 // 3 = pipelined, 2 x 128-row tile pipelines per CTA (default; decoder hidden layer on the tensor core), 4 = the same
 // kernel with 4 x 64-row pipelines, 1 = phase-structured, 2 = warp-specialised, 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 4) : 3; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 5) : 5; }
     return g_step_kernel;
 }
 
@@ -1779,6 +1818,21 @@ static int r_state_choice() {
     return g_r_state;
 }
 
+// persistent (cooperative, one launch per rollout) vs one launch per Euler step: -1 = by batch size (default), 0 / 1 forced
+static int g_persistent = -2;
+static int persistent_choice() {
+    if (g_persistent < -1) { const char* e = getenv("GNODE_PERSISTENT"); g_persistent = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
+    return g_persistent;
+}
+
+static bool persistent_forced() { return persistent_choice() == 1; }
+
+// GNODE_DBG (timing experiments of the older step kernels) is read once per process
+static int debug_flags() {
+    static const int flags = getenv("GNODE_DBG") ? atoi(getenv("GNODE_DBG")) : 0;
+    return flags;
+}
+
 // the dual kernel emits probs[k] of its INPUT state and needs the hid_i side buffer (tensor-core variants only)
 static bool use_dual() { return (current_variant() & VAR_TC) && step_kernel_choice() >= 3; }
 
@@ -1786,6 +1840,11 @@ template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
     if (MODE == MODE_STEP && use_dual()) {
+        if (step_kernel_choice() >= 5 && a.use_tma == 2) {      // TMA-fed S stream
+            const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
+            return fast ? (rf ? launch_step_stream<true, true>(b, a, stream) : launch_step_stream<true, false>(b, a, stream))
+                        : (rf ? launch_step_stream<false, true>(b, a, stream) : launch_step_stream<false, false>(b, a, stream));
+        }
         if (step_kernel_choice() == 4) return (var & VAR_FASTSIG) ? launch_step_dual<true, 4, false>(b, a, stream) : launch_step_dual<false, 4, false>(b, a, stream);
         if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
         return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, false>(b, a, stream) : launch_step_dual<false, 2, false>(b, a, stream);
@@ -1845,7 +1904,7 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
-    if (kernel < 0 || kernel > 4) { set_error("gnode_set_step_kernel: kernel must be 0..4"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 5) { set_error("gnode_set_step_kernel: kernel must be 0..5"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }
@@ -1856,6 +1915,12 @@ extern "C" int gnode_set_r_state(int hidden) {
     return GNODE_OK;
 }
 extern "C" int gnode_get_r_state(void) { return r_state_choice(); }
+extern "C" int gnode_set_persistent(int mode) {
+    if (mode < -1 || mode > 1) { set_error("gnode_set_persistent: -1 = by batch size, 0 = one launch per step, 1 = one cooperative launch"); return GNODE_ERR_ARG; }
+    g_persistent = mode;
+    return GNODE_OK;
+}
+extern "C" int gnode_get_persistent(void) { return persistent_choice(); }
 extern "C" int gnode_debug_phase_cycles(long long* out8) {
     if (!out8) return GNODE_ERR_ARG;
     for (int i = 0; i < 8; ++i) out8[i] = 0;
@@ -1872,32 +1937,66 @@ extern "C" size_t gnode_rollout_workspace_bytes(gnode_batch_t b, int with_traj) 
     const size_t M = (size_t)b->M;
     size_t bytes = 2 * align_up(M * sizeof(float), 256);          // beta, gamma
     bytes += 4096;                                                // tile-scheduler counters (one int per launch)
-    bytes += 4096;                                                // device copy of the step sizes (persistent rollout)
+    bytes += 4096;                                                // device copy of the step sizes (persistent rollout, non-uniform grids)
+    bytes += 4096;                                                // device copy of the output slots (persistent rollout, irregular selections)
     bytes += 2 * align_up((M + 1) * H * sizeof(float), 256);      // I' ping-pong (+ one all-zero row each)
     bytes += 2 * align_up(M * 4 * sizeof(float), 256);            // hid_i, hid_r: linear3 pre-activations of the I / R block
     if (!with_traj) bytes += 2 * align_up(3 * M * H * sizeof(float), 256);  // state ping-pong
     return bytes;
 }
 
-extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
-                                     int32_t T, const float* dt_host, float* traj, float* probs,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
-    if (!b || !x || !p || !probs || !workspace || T < 1 || ldx < 5 || (T > 1 && !dt_host)) {
-        set_error("gnode_rollout_forward: bad arguments (T=%d ldx=%lld)", T, (long long)ldx);
+namespace gnode {
+
+// the handle's device must be the calling thread's current device (kernels are launched on it with the handle's pointers)
+int check_current_device(const gnode_batch* b, const char* what) {
+    int dev = -1;
+    GN_CUDA(cudaGetDevice(&dev));
+    if (dev != b->device) {
+        set_error("%s: the batch lives on device %d but the current device is %d", what, b->device, dev);
         return GNODE_ERR_ARG;
     }
+    return GNODE_OK;
+}
+
+int make_out_sel(int T, const int32_t* out_steps, int32_t n_out, OutSel* o, const char* what) {
+    o->slot.assign((size_t)T, -1);
+    if (!out_steps) {
+        for (int k = 0; k < T; ++k) o->slot[k] = k;
+        o->n_out = T; o->start = 0; o->stride = 1; o->arithmetic = true;
+        return GNODE_OK;
+    }
+    if (n_out < 1 || n_out > T) { set_error("%s: n_out = %d outside [1, T = %d]", what, n_out, T); return GNODE_ERR_ARG; }
+    for (int i = 0; i < n_out; ++i) {
+        if (out_steps[i] < 0 || out_steps[i] >= T || (i > 0 && out_steps[i] <= out_steps[i - 1])) {
+            set_error("%s: out_steps must be strictly ascending grid indices in [0, %d)", what, T);
+            return GNODE_ERR_ARG;
+        }
+        o->slot[out_steps[i]] = i;
+    }
+    o->n_out = n_out; o->start = out_steps[0];
+    o->stride = n_out > 1 ? out_steps[1] - out_steps[0] : 1;
+    o->arithmetic = true;
+    for (int i = 1; i < n_out; ++i) if (out_steps[i] - out_steps[i - 1] != o->stride) o->arithmetic = false;
+    return GNODE_OK;
+}
+
+static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p, int32_t T,
+                                const float* dt_host, const OutSel& sel, float* traj, float* probs, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
     if (workspace_bytes < gnode_rollout_workspace_bytes(b, traj != nullptr)) {
         set_error("gnode_rollout_forward: workspace too small (%zu < %zu)", workspace_bytes,
                   gnode_rollout_workspace_bytes(b, traj != nullptr));
         return GNODE_ERR_ARG;
     }
-    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_current_device(b, "gnode_rollout_forward");
+    if (rc) return rc;
     const size_t M = (size_t)b->M;
     unsigned char* ws = (unsigned char*)workspace;
     float* beta = (float*)ws;  ws += align_up(M * sizeof(float), 256);
     float* gamma = (float*)ws; ws += align_up(M * sizeof(float), 256);
     int* counters = (int*)ws;  ws += 4096;
     float* dt_dev = (float*)ws; ws += 4096;
+    int* slot_dev = (int*)ws; ws += 4096;
     GN_CUDA(cudaMemsetAsync(counters, 0, 4096, stream));
     float* ip[2];
     ip[0] = (float*)ws; ws += align_up((M + 1) * H * sizeof(float), 256);
@@ -1912,16 +2011,18 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
         st[1] = (float*)ws;
     }
     auto state = [&](int k) -> float* { return traj ? traj + (size_t)k * 3 * M * H : st[k & 1]; };
+    auto out = [&](int k) -> float* { return sel.slot[k] >= 0 ? probs + (size_t)sel.slot[k] * M * 3 : nullptr; };
 
-    StepArgs a;
+    StepArgs a{};
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = beta; a.gamma = gamma;
     a.x = x; a.ldx = ldx;
     a.y_in = nullptr; a.ip_in = nullptr;
     a.y_out = state(0); a.ip_out = ip[0];
-    a.probs = probs; a.dt = 0.f;
-    a.dbg = getenv("GNODE_DBG") ? atoi(getenv("GNODE_DBG")) : 0;
+    a.probs = out(0); a.dt = 0.f;
+    a.out_slot = nullptr; a.out_start = sel.start; a.out_stride = sel.stride; a.n_out = sel.n_out;
+    a.dbg = debug_flags();
     a.tbuf = nullptr;
     if (a.dbg & 128) {
         if (!g_tbuf) { GN_CUDA(cudaMalloc(&g_tbuf, 64)); GN_CUDA(cudaMemset(g_tbuf, 0, 64)); }
@@ -1929,54 +2030,167 @@ extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ld
     }
     a.counter = (a.dbg & 64) ? nullptr : counters;
     const bool dual = use_dual();
+    const bool stream_kernel = dual && step_kernel_choice() >= 5;
     a.use_tma = 0;
     CUtensorMap tm_ip[2];
     const bool have_tma = dual && !(a.dbg & 32768) && encode_rows_map(&tm_ip[0], ip[0], M) && encode_rows_map(&tm_ip[1], ip[1], M);
     a.hid_i = dual ? hid_i : nullptr;
-    const bool rfree = dual && !traj && T > 1 && step_kernel_choice() == 3 && r_state_choice() == 1;
+    const bool rfree = dual && !traj && T > 1 && step_kernel_choice() != 4 && r_state_choice() == 1;
     a.hid_r = rfree ? hid_r : nullptr;
-    int rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
+    rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
     a.n_steps = 0; a.k0 = 0;
     // Persistent rollout: ONE cooperative launch runs all T-1 Euler steps with a grid barrier between them (no per-step
     // launch, weight operands and TMEM stay resident).
     // Default: batches of up to 16 tiles per pipeline (~600k rows), where a launch per step costs >= 2 % ; larger batches
     // keep one launch per step (the persistent variant reads its per-step operands from shared memory: -1 % there).
-    // GNODE_PERSISTENT=1 / 0 forces it on / off.
-    static const int persistent_mode = getenv("GNODE_PERSISTENT") ? atoi(getenv("GNODE_PERSISTENT")) : -1;
+    // gnode_set_persistent / GNODE_PERSISTENT=1 / 0 forces it on / off.
+    const int persistent_mode = persistent_choice();
     const bool persistent_ok = persistent_mode < 0 ? b->n_tiles <= 32 * b->sm_count : persistent_mode != 0;
     int coop = 0;
     if (dual && persistent_ok && T > 2 && T - 1 <= 1023 && !(a.dbg & 64))
         GN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device));
     if (coop) {
-        GN_CUDA(cudaMemcpyAsync(dt_dev, dt_host, sizeof(float) * (size_t)(T - 1), cudaMemcpyHostToDevice, stream));
+        // step sizes / output slots: carried in the kernel parameters when the grid is uniform and the selection an
+        // arithmetic progression (the reference's np.arange grid and int(i/deltaT) selection); otherwise copied to the
+        // workspace (a pageable source makes that copy block the host until it is staged)
+        bool uniform = true;
+        for (int k = 1; k + 1 < T; ++k) if (dt_host[k] != dt_host[0]) uniform = false;
+        a.dt_dev = nullptr;
+        if (!uniform) {
+            GN_CUDA(cudaMemcpyAsync(dt_dev, dt_host, sizeof(float) * (size_t)(T - 1), cudaMemcpyHostToDevice, stream));
+            a.dt_dev = dt_dev;
+        }
+        if (!sel.arithmetic) {
+            GN_CUDA(cudaMemcpyAsync(slot_dev, sel.slot.data(), sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, stream));
+            a.out_slot = slot_dev;
+        }
         a.n_steps = T - 1; a.k0 = 0;
         a.traj = traj; a.st[0] = st[0]; a.st[1] = st[1];
         a.ipb[0] = ip[0]; a.ipb[1] = ip[1];
-        a.probs_base = probs; a.dt_dev = dt_dev; a.counters = counters;
+        a.probs_base = probs; a.counters = counters;
         a.use_tma = have_tma ? 1 : 0;
         if (have_tma) { a.tm_ipb[0] = tm_ip[0]; a.tm_ipb[1] = tm_ip[1]; }
+        if (have_tma && stream_kernel) {                  // S_k tiles by TMA: maps over the S planes (or the whole trajectory)
+            const bool ok = traj ? encode_rows_map(&a.tm_sp[0], traj, (size_t)T * 3 * M)
+                                 : (encode_rows_map(&a.tm_sp[0], st[0], M) && encode_rows_map(&a.tm_sp[1], st[1], M));
+            if (ok && (!traj || (size_t)T * 3 * M < ((size_t)1 << 31))) a.use_tma = 2;
+        }
         a.y_in = state(0); a.y_out = state(1); a.ip_in = ip[0]; a.ip_out = ip[1]; a.probs = nullptr; a.dt = dt_host[0];
         rc = launch_step<MODE_STEP>(b, a, stream);
-        if (rc) return rc;
-    } else
+        if (rc == GNODE_ERR_CUDA && !persistent_forced()) {
+            // e.g. cudaErrorCooperativeLaunchTooLarge under MPS / green-context SM limits: clear it, one launch per step
+            (void)cudaGetLastError();
+            coop = 0;
+            a.n_steps = 0;
+        } else if (rc) return rc;
+    }
+    if (!coop)
     for (int k = 0; k + 1 < T; ++k) {
         a.y_in = state(k); a.y_out = state(k + 1);
         a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
+        a.use_tma = 0;
         if (have_tma) { a.use_tma = 1; a.tm_ip_out = tm_ip[(k + 1) & 1]; }
+        if (have_tma && stream_kernel && encode_rows_map(&a.tm_s_in, state(k), M)) a.use_tma = 2;
         // dual kernel: step k decodes its input state k (k = 0 is the encoder's); the others decode their output
-        a.probs = dual ? (k > 0 ? probs + (size_t)k * M * 3 : nullptr) : probs + (size_t)(k + 1) * M * 3;
+        a.probs = dual ? (k > 0 ? out(k) : nullptr) : out(k + 1);
         a.dt = dt_host[k];
         a.counter = (k + 1 < 1024 && !(a.dbg & 64)) ? counters + (k + 1) : nullptr;
         rc = launch_step<MODE_STEP>(b, a, stream);
         if (rc) return rc;
     }
-    if (dual && T > 1) {                                   // the last grid state
+    if (dual && T > 1 && out(T - 1)) {                     // the last grid state
         const int grid = (int)std::min<int64_t>(((int64_t)M + 15) / 16, (int64_t)b->sm_count * 16);
-        decode_kernel<<<grid, 256, 0, stream>>>(state(T - 1), probs + (size_t)(T - 1) * M * 3, (int)M, *p, a.hid_r);
+        decode_kernel<<<grid, 256, 0, stream>>>(state(T - 1), out(T - 1), (int)M, *p, a.hid_r);
         GN_LAUNCH_CHECK();
     }
     return GNODE_OK;
+}
+
+// ---- N4: compact trial descriptors -> the five live columns of the reference's dense input block -----------------
+// x[r] = {S0, I0, R0, beta, gamma} with I0 = 1 on the seeds, S0 = 1 - I0, R0 = 0 (ode_nn_ngraph_sim.py:371-390)
+__global__ void __launch_bounds__(256) expand_trials_kernel(const GnBatchView bv, const float* __restrict__ beta,
+                                                            const float* __restrict__ gamma, float* __restrict__ x, int64_t ldx) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < bv.M; r += (int64_t)gridDim.x * blockDim.x) {
+        const int i = find_instance(bv, r);
+        float* xr = x + (size_t)r * ldx;
+        xr[0] = 1.f; xr[1] = 0.f; xr[2] = 0.f; xr[3] = beta[i]; xr[4] = gamma[i];
+    }
+}
+__global__ void __launch_bounds__(256) seed_trials_kernel(const GnBatchView bv, const int32_t* __restrict__ seeds,
+                                                          const int32_t* __restrict__ seed_ptr, float* __restrict__ x, int64_t ldx) {
+    const int total = seed_ptr[bv.n_inst];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int lo = 0, hi = bv.n_inst - 1;                      // instance that owns seed entry e
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seed_ptr[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const GnInstance I = bv.inst[lo];
+        const int s = seeds[e];
+        if (s < 0 || s >= I.n) continue;                     // out of range: ignored (the host wrapper validates)
+        float* xr = x + (size_t)(I.row0 + s) * ldx;
+        xr[0] = 0.f; xr[1] = 1.f;
+    }
+}
+
+}  // namespace gnode
+
+extern "C" int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                     int32_t T, const float* dt_host, float* traj, float* probs,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+    return gnode_rollout_forward_sel(b, x, ldx, p, T, dt_host, nullptr, 0, traj, probs, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int gnode_rollout_forward_sel(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                         int32_t T, const float* dt_host, const int32_t* out_steps, int32_t n_out,
+                                         float* traj, float* probs, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!b || !x || !p || !probs || !workspace || T < 1 || ldx < 5 || (T > 1 && !dt_host)) {
+        set_error("gnode_rollout_forward: bad arguments (T=%d ldx=%lld)", T, (long long)ldx);
+        return GNODE_ERR_ARG;
+    }
+    OutSel sel;
+    int rc = make_out_sel(T, out_steps, n_out, &sel, "gnode_rollout_forward_sel");
+    if (rc) return rc;
+    return rollout_forward_impl(b, x, ldx, p, T, dt_host, sel, traj, probs, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int gnode_expand_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr, const float* beta,
+                                   const float* gamma, float* x, int64_t ldx, void* stream_) {
+    if (!b || !seeds || !seed_ptr || !beta || !gamma || !x || ldx < 5) {
+        set_error("gnode_expand_trials: bad arguments (ldx=%lld)", (long long)ldx);
+        return GNODE_ERR_ARG;
+    }
+    int rc = check_current_device(b, "gnode_expand_trials");
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int grid = (int)std::min<int64_t>((b->M + 255) / 256, (int64_t)b->sm_count * 8);
+    expand_trials_kernel<<<grid, 256, 0, stream>>>(gn_view(b), beta, gamma, x, ldx);
+    GN_LAUNCH_CHECK();
+    seed_trials_kernel<<<std::max(1, std::min(b->n_inst, b->sm_count * 8)), 256, 0, stream>>>(gn_view(b), seeds, seed_ptr, x, ldx);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
+extern "C" size_t gnode_rollout_trials_workspace_bytes(gnode_batch_t b, int with_traj) {
+    if (!b) return 0;
+    return gnode_rollout_workspace_bytes(b, with_traj) + align_up((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), 256);
+}
+
+extern "C" int gnode_rollout_forward_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr,
+                                            const float* beta, const float* gamma, const gnode_params_t* p, int32_t T,
+                                            const float* dt_host, const int32_t* out_steps, int32_t n_out, float* traj,
+                                            float* probs, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!b || !workspace || workspace_bytes < gnode_rollout_trials_workspace_bytes(b, traj != nullptr)) {
+        set_error("gnode_rollout_forward_trials: workspace missing or too small");
+        return GNODE_ERR_ARG;
+    }
+    const size_t xbytes = align_up((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), 256);
+    float* x = (float*)workspace;
+    int rc = gnode_expand_trials(b, seeds, seed_ptr, beta, gamma, x, GNODE_TRIAL_LDX, stream_);
+    if (rc) return rc;
+    return gnode_rollout_forward_sel(b, x, GNODE_TRIAL_LDX, p, T, dt_host, out_steps, n_out, traj, probs,
+                                     (unsigned char*)workspace + xbytes, workspace_bytes - xbytes, stream_);
 }
 
 extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* beta, const float* gamma,
@@ -1986,7 +2200,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
         return GNODE_ERR_ARG;
     }
     cudaStream_t stream = (cudaStream_t)stream_;
-    StepArgs a;
+    StepArgs a{};
     a.bv = gn_view(b);
     a.p = *p;
     a.beta = const_cast<float*>(beta); a.gamma = const_cast<float*>(gamma);

@@ -1,0 +1,560 @@
+// step_stream_kernel: the fused Euler step with the contiguous S_k stream fed by TMA (included by gnode_forward.cu).
+//
+// Same tile pipeline as step_dual_kernel (one 1024-thread CTA per SM = two 512-thread pipelines of 128-row tiles that
+// share the [W; W3] operand), with three changes that take bytes and LSU work out of the step:
+//   * the S_k tile of the NEXT tile is fetched by two TMA tensor loads (cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of
+//     32 x 128 fp32, SASS UTMALDG) issued by the otherwise idle metadata thread as soon as GEMM2 of the current tile
+//     has finished reading the operand buffer: no registers, no LSU wavefronts and no L1 lines for this stream, and the
+//     load's latency hides behind the I' epilogue and the tile turn-over;
+//   * the tile lands directly in the canonical UMMA K-major operand layout and the RAW fp32 tile is the `hi` operand:
+//     tcgen05.mma kind::tf32 reads the top 19 bits of each 32-bit element, i.e. hi = trunc_tf32(x) implicitly, and the
+//     threads only write lo = rna_tf32(x - trunc_tf32(x)). The raw tile stays in shared memory until the row update
+//     reads S_k from it: S_k is read from HBM/L2 ONCE per step (step_dual_kernel: twice);
+//   * the neighbour sum is folded into S' in place (AI * S', the first product of dS, ode_nn_ngraph_sim.py:75), so the
+//     parked value needs no buffer of its own. (Measured and rejected: the gathering half-warp performing the whole row
+//     update with its own I_k / I'_k rows requested together with the neighbour rows -- 1.64e9 vs 1.66e9 node-steps/s,
+//     profiles/r2b_ab_step_kernels.log.)
+// Arithmetic of the update is the reference's, op for op; S, I, R and the probabilities are bitwise
+// those of step_dual_kernel except for the A-operand split (truncated hi: per-product error 1.5 * 2^-22 instead of 2^-22).
+#pragma once
+
+namespace gnode {
+
+struct StreamCfg {
+    static constexpr int PT = D_THREADS / 2;               // threads per pipeline
+    static constexpr int TR = 128;                         // tile rows = UMMA M
+    static constexpr int RSTEP = PT / 16;                  // rows per pass of the row-per-half-warp loops (32)
+    static constexpr int PASS = RSTEP * 128;               // byte offset between the passes' rows in an operand tile
+    static constexpr int CAP = 3 * PT;                     // colidx entries staged per tile
+    static constexpr int HUB_DEG = 512;
+    static constexpr int KBLK = TR * 128;                  // bytes of one K-block (32 fp32) of the A operand
+    static constexpr int P_X = 0;                          // raw S_k (= hi operand) -> I_{k+1} raw (= hi operand of GEMM2)
+    static constexpr int P_L = 2 * KBLK;                   // lo operand -> S' -> AI * S' -> lo of I_{k+1} -> I'_{k+1} staging
+    static constexpr int P_MBAR = 4 * KBLK;                // GEMM mbarrier (8) + row-pair counter (4) + pad (4) + S-load mbarrier (8)
+    static constexpr int P_META = P_MBAR + 32;             // DTileMeta of the coming tile (48 B)
+    static constexpr int P_BG = P_META + 48;               // beta[TR], gamma[TR]
+    static constexpr int P_RP = P_BG + 2 * TR * 4;         // rowptr slice [TR + 1] (+pad, hub mask)
+    static constexpr int P_HS = P_RP + TR * 4 + 32;        // hid(S_k) [TR][4]
+    static constexpr int P_HR = P_HS + TR * 16;            // hid(R_k) / W3 I'_k [TR][4]
+    static constexpr int P_CI = P_HR + TR * 16;            // colidx slice + 64 B over-read pad
+    static constexpr int P_BYTES = ((P_CI + CAP * 4 + 64 + 1023) / 1024) * 1024;
+    static constexpr int TOTAL = D_SHARED + 2 * P_BYTES + 1024;
+    static constexpr int TMEM_COLS = 256;
+    static_assert(TOTAL + 1024 <= 200704, "stay inside the 196 KB shared-memory carve-out (60 KB of L1 left)");
+    static __device__ __forceinline__ int sw(int r, int c4) { return (c4 >> 3) * KBLK + (r << 7) + (((c4 & 7) ^ (r & 7)) << 4); }
+};
+
+// TMA tensor load of one box (global -> shared memory), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* smem_dst, uint64_t* bar, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(umma::smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(umma::smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// lo part of the A operand when the raw fp32 value is the hi operand: the tensor core uses the top 19 bits
+// (sign, 8 exponent, 10 mantissa bits); the residual is exact in fp32 and rounded to tf32
+__device__ __forceinline__ float tf32_lo_of_raw(float x) {
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return umma::tf32_rna(x - hi);
+}
+__device__ __forceinline__ float4 tf32_lo_of_raw4(float4 x) {
+    return make_float4(tf32_lo_of_raw(x.x), tf32_lo_of_raw(x.y), tf32_lo_of_raw(x.z), tf32_lo_of_raw(x.w));
+}
+
+// neighbour sum specialised by the pair's larger degree: 1..MAXR rows in one round trip, longer rows in rounds of 8
+template <int MAXR>
+__device__ __forceinline__ float4 gather_smem_zm(const float* __restrict__ lane_base, const int* cp, int deg, int zrow, uint64_t pol) {
+    const int degm = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; degm - j > MAXR; j += 8) gather_exact<8>(acc, lane_base, cp, j, deg, zrow, pol);
+    switch (degm - j) {
+        case 12: if (MAXR >= 12) gather_exact<12>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 11: if (MAXR >= 11) gather_exact<11>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 10: if (MAXR >= 10) gather_exact<10>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 9: if (MAXR >= 9) gather_exact<9>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 8: gather_exact<8>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 7: gather_exact<7>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 6: gather_exact<6>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 5: gather_exact<5>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 4: gather_exact<4>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 3: gather_exact<3>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 2: gather_exact<2>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        case 1: gather_exact<1>(acc, lane_base, cp, j, deg, zrow, pol); break;
+        default: break;
+    }
+    return acc;
+}
+
+// per-step operands (persistent rollout: derived per Euler step by one thread)
+struct SStep {
+    const float* y_in; float* y_out;
+    const float* ip_in; float* ip_out;
+    float* probs; int* counter;
+    const CUtensorMap* tm;        // I'_{k+1} store
+    const CUtensorMap* tms;       // S_k load
+    int srow0;                    // row coordinate of the S plane's first row in tms
+    float dt;
+};
+
+template <bool FAST, bool PERSIST, bool RF>
+__global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_constant__ StepArgs a) {
+    using C = StreamCfg;
+    constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x;
+    const int half = __shfl_sync(0xffffffffu, tid / PT, 0);          // pipeline index, provably warp-uniform
+    const int t = tid & (PT - 1), lane = t & 31;
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);            // warp index inside the pipeline
+    const int l = t & 15, hw = t >> 4;
+    unsigned char* hb = smem + D_SHARED + half * C::P_BYTES;
+    unsigned char* Xs = hb + C::P_X;
+    unsigned char* Ls = hb + C::P_L;
+    float* bs = reinterpret_cast<float*>(smem + D_B);
+    float* W3s = reinterpret_cast<float*>(smem + D_W3);
+    float* small = reinterpret_cast<float*>(smem + D_SMALL);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + D_TSLOT);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(hb + C::P_MBAR);
+    int* row_ctr = reinterpret_cast<int*>(hb + C::P_MBAR + 8);
+    uint64_t* sbar = reinterpret_cast<uint64_t*>(hb + C::P_MBAR + 16);
+    DTileMeta* meta = reinterpret_cast<DTileMeta*>(hb + C::P_META);
+    float* bg_s = reinterpret_cast<float*>(hb + C::P_BG);
+    int* rp_s = reinterpret_cast<int*>(hb + C::P_RP);
+    float* hs_s = reinterpret_cast<float*>(hb + C::P_HS);
+    float* hr_s = reinterpret_cast<float*>(hb + C::P_HR);
+    int* ci_s = reinterpret_cast<int*>(hb + C::P_CI);
+    unsigned* hub_mask = reinterpret_cast<unsigned*>(rp_s + TR + 2);
+    const int bar_id = 1 + half;
+#define HSYNC() umma::bar_sync(bar_id, PT)
+
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    const int n_tiles = a.bv.n_tiles;
+    const int off0 = C::sw(hw, l);
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first();
+
+    SStep* stp = reinterpret_cast<SStep*>(smem + D_TSLOT + 16);
+    static_assert(D_TSLOT + 16 + sizeof(SStep) <= D_SHARED, "SStep overflows the shared part");
+#define STP(f) (PERSIST ? stp->f : a.f)
+#define STP_TM() (PERSIST ? stp->tm : &a.tm_ip_out)
+#define STP_TMS() (PERSIST ? stp->tms : &a.tm_s_in)
+#define STP_SROW0() (PERSIST ? stp->srow0 : 0)
+
+    // one thread: draw the next sequence number and resolve its metadata (3 dependent loads of small tables)
+    auto fetch_meta = [&](int k) {
+        const int first = (int)blockIdx.x + half * (int)gridDim.x;
+        const int seq = k == 0 ? first : (STP(counter) ? 2 * (int)gridDim.x + atomicAdd(STP(counter), 1) : first + 2 * k * (int)gridDim.x);
+        DTileMeta m;
+        m.seq = seq; m.rowptr = nullptr; m.colidx = nullptr;
+        m.tile0 = 0; m.nrows = 0; m.i_row0 = 0; m.single = 0; m.ebase = 0; m.ecnt = 0; m.inst0 = 0;
+        if (seq < n_tiles) {
+            const int tile = a.bv.tile_order[seq];
+            const int4 tm = a.bv.tile_meta[tile];                     // {ebase, ecnt, inst0, single}
+            const GnInstance I = a.bv.inst[tm.z];
+            m.tile0 = tile * TILE;
+            m.nrows = max(0, min(TR, M - m.tile0));
+            m.i_row0 = I.row0; m.single = tm.w; m.ebase = tm.x; m.ecnt = tm.y; m.inst0 = tm.z;
+            m.rowptr = I.rowptr + (m.tile0 - I.row0);
+            m.colidx = I.colidx;
+        }
+        *meta = m;
+    };
+    // the same thread: request the S_k rows of that tile (raw fp32, operand layout) into Xs
+    auto issue_s_load = [&]() {
+        if (meta->seq < n_tiles) {
+            mbar_expect_tx(sbar, 2 * C::KBLK);
+            const int r0 = STP_SROW0() + meta->tile0;
+            tma_load_2d(STP_TMS(), Xs, sbar, 0, r0, pol_stream);
+            tma_load_2d(STP_TMS(), Xs + C::KBLK, sbar, 32, r0, pol_stream);
+        }
+    };
+
+    umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
+    if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
+    if (t == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(sbar, 1); }
+    umma::fence_before_sync();
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
+    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+    if (tid == 0) small[8] = a.p.s2_b[0];
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tslot + (uint32_t)half * 128u;             // this pipeline's [128 x 80] fp32 accumulator
+    const uint32_t whi = umma::smem_u32(smem + D_WHI), wlo = umma::smem_u32(smem + D_WLO);
+    const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
+    const int q = warp & 3, cq = warp >> 2;                           // TMEM lane quarter, 16-column block
+    const int erow = q * 32 + lane;                                   // tile row this thread owns in the epilogues
+    uint32_t phase = 0, sphase = 0;
+    int kfetch = 1;
+    const int n_steps = PERSIST ? max(a.n_steps, 1) : 1;
+
+    const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
+
+#pragma unroll 1
+    for (int step = 0; step < n_steps; ++step) {
+    if (PERSIST) {
+        if (tid == 0) {
+            SStep d;
+            d.y_in = a.y_in; d.y_out = a.y_out; d.ip_in = a.ip_in; d.ip_out = a.ip_out;
+            d.probs = a.probs; d.counter = a.counter; d.tm = &a.tm_ip_out; d.tms = &a.tm_s_in; d.srow0 = 0; d.dt = a.dt;
+            if (a.n_steps > 0) {                              // persistent rollout: operands of Euler step ks
+                const int ks = a.k0 + step;
+                const size_t plane3 = 3 * (size_t)M * H;
+                d.y_in = a.traj ? a.traj + (size_t)ks * plane3 : a.st[ks & 1];
+                d.y_out = a.traj ? a.traj + (size_t)(ks + 1) * plane3 : a.st[(ks + 1) & 1];
+                d.ip_in = a.ipb[ks & 1]; d.ip_out = a.ipb[(ks + 1) & 1];
+                const int slot = out_slot_of(a, ks);
+                d.probs = (ks > 0 && slot >= 0) ? a.probs_base + (size_t)slot * M * 3 : nullptr;
+                d.dt = a.dt_dev ? a.dt_dev[ks] : a.dt;
+                d.counter = a.counters ? a.counters + ks + 1 : nullptr;
+                d.tm = &a.tm_ipb[(ks + 1) & 1];
+                d.tms = a.traj ? &a.tm_sp[0] : &a.tm_sp[ks & 1];
+                d.srow0 = a.traj ? ks * 3 * M : 0;
+            }
+            *stp = d;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        fetch_meta(0);
+        if (PERSIST) asm volatile("fence.proxy.async;" ::: "memory");   // state rows written by other SMs (generic proxy) -> TMA reads
+        issue_s_load();
+    }
+    kfetch = 1;
+    HSYNC();
+    for (;;) {
+        const DTileMeta m = *meta;                                    // written before the last barrier passed
+        if (m.seq >= n_tiles) break;
+        const int tile0 = m.tile0, nrows = m.nrows, i_row0 = m.i_row0, ebase = m.ebase;
+        const bool single = (m.single & 1) != 0;
+        const bool relay = (m.single & 2) != 0;                       // the tile has isolated hub rows (host cost model)
+        const float dt = STP(dt);
+
+        // ---- P1: CSR slice, beta/gamma -> smem; lo operand of the TMA-loaded S_k tile
+        {
+            int rpv = 0, civ[3] = {0, 0, 0};
+            float bgv = 0.f;
+            const int ecnt = min(m.ecnt, C::CAP);
+            if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
+            if (single) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) civ[u] = __ldg(m.colidx + ebase + t + u * PT);
+            }
+            if (t >= PT / 2 && t < PT / 2 + nrows) bgv = a.beta[tile0 + t - PT / 2];
+            if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
+            umma::mbar_wait(sbar, sphase); sphase ^= 1;               // the S_k tile has landed in Xs
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sts4(Ls, off0 + i * PASS, tf32_lo_of_raw4(lds4(Xs, off0 + i * PASS)));
+            umma::fence_proxy_async();
+            if (t == 0) *row_ctr = 0;
+            if (t < TR / 32) hub_mask[t] = 0u;
+            if (single && t <= nrows) rp_s[t] = rpv;
+            if (single) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = civ[u];   // instance-local ids
+            }
+            if (t >= PT / 2 && t < PT / 2 + nrows) bg_s[t - PT / 2] = bgv;
+            if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bg_s[TR + t - 3 * PT / 4] = bgv;
+        }
+        HSYNC();                                                                // S1
+        // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
+        if (t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
+        umma::mbar_wait_suspend(mbar, phase); phase ^= 1;
+        umma::fence_after_sync();
+        {
+            float v[16];
+            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+                float4 o;
+                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                sts4(Ls, C::sw(erow, 4 * cq + j), o);
+            }
+            if (cq == 0) {
+                float hv[4];
+                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                *reinterpret_cast<float4*>(hs_s + 4 * erow) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            }
+        }
+        umma::fence_before_sync();
+        HSYNC();                                                                // S2
+
+        const bool dec = RF || STP(probs) != nullptr;
+        // own-row operands that still come from HBM/L2: I_k, I'_k (and R_k when the R plane is carried)
+        auto load_own = [&](int rr, bool ok, float4& iv, float4& rv, float4& ipo) {
+            iv = make_float4(1.f, 1.f, 1.f, 1.f); rv = iv; ipo = iv;
+            if (ok) {
+                const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
+                iv = ldg4_hint(STP(y_in) + plane + off, pol_stream);
+                if (!RF) rv = ldg4_hint(STP(y_in) + 2 * plane + off, pol_stream);
+                ipo = ldg4_hint(STP(ip_in) + off, pol_keep);
+            }
+        };
+        // SIR update of tile row rr from tp = AI * S' (`ok` is uniform per half-warp): stores S,I(,R)_{k+1}; I_{k+1}
+        // raw / lo -> operand tiles; returns the lane's partial linear3 products of R_k (RF: of I'_k) in hv
+        auto update_row = [&](int rr, bool ok, float4 tp, float4 iv, float4 rv, float4 ipo,
+                              float4 w30, float4 w31, float4 w32, float4 w33, float (&hv)[4]) {
+            hv[0] = 0.f; hv[1] = 0.f; hv[2] = 0.f; hv[3] = 0.f;
+            if (ok) {
+                const int o = C::sw(rr, l);
+                const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
+                const float4 s = lds4(Xs, o);
+                const float nbe = -bg_s[rr], ga = bg_s[TR + rr];
+                float4 sn, in_, rn;
+#define GN_COMP(c)                                                                  \
+    {                                                                               \
+        const float dS = __fmul_rn(nbe, tp.c);                                      \
+        const float dR = __fmul_rn(ga, ipo.c);                                      \
+        const float dI = __fsub_rn(-dS, dR);                                        \
+        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
+        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
+        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
+    }
+                GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
+#undef GN_COMP
+                stg4_hint(STP(y_out) + off, sn, pol_stream);
+                stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
+                if (!RF) stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
+                sts4(Xs, o, in_);                                    // raw = hi operand of GEMM2
+                sts4(Ls, o, tf32_lo_of_raw4(in_));
+                if (dec) {
+                    const float4 dv = RF ? ipo : rv;
+                    hv[0] = dot4(dv, w30); hv[1] = dot4(dv, w31); hv[2] = dot4(dv, w32); hv[3] = dot4(dv, w33);
+                }
+            }
+        };
+        // halving butterfly over the 16 lanes of the row: lanes 0 / 4 / 8 / 12 end with hid[0 / 1 / 2 / 3]
+        // (full-mask shuffles: all 32 lanes of the warp call it)
+        auto hid_bfly = [&](int rr, bool ok, const float (&hv)[4]) {
+            if (dec) {
+                const float a0 = (b3 ? hv[2] : hv[0]) + __shfl_xor_sync(0xffffffffu, b3 ? hv[0] : hv[2], 8);
+                const float a1 = (b3 ? hv[3] : hv[1]) + __shfl_xor_sync(0xffffffffu, b3 ? hv[1] : hv[3], 8);
+                float c = (b2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b2 ? a0 : a1, 4);
+                c += __shfl_xor_sync(0xffffffffu, c, 2);
+                c += __shfl_xor_sync(0xffffffffu, c, 1);
+                if (ok && (l & 3) == 0) hr_s[4 * rr + (l >> 2)] = c;
+            }
+        };
+        // what the gathering half-warp does with the finished neighbour sum of row rr: AI * S' replaces S' in place
+        auto finish_row = [&](int rr, bool ok, float4 acc) {
+            const int o = C::sw(rr, l);
+            const float4 sp = lds4(Ls, o);
+            if (ok) sts4(Ls, o, make_float4(__fmul_rn(acc.x, sp.x), __fmul_rn(acc.y, sp.y), __fmul_rn(acc.z, sp.z), __fmul_rn(acc.w, sp.w)));
+        };
+
+        // ---- P3a: neighbour sums AI (sequential, ascending columns), folded into S' in place
+        {
+            const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
+            const int zrow = M - i_row0;                     // the all-zero row that follows the I' rows
+            if (single) {
+                const bool static_rows = m.ecnt <= C::CAP;
+                int p = 0, sj = 1;
+                if (static_rows) p = warp;
+                else {
+                    if (lane == 0) p = atomicAdd(row_ctr, 1);
+                    p = __shfl_sync(0xffffffffu, p, 0);
+                }
+                while (p < TR / 2) {
+                    int pn = 0;
+                    if (static_rows) { pn = warp + (PT / 32) * sj; ++sj; }
+                    else if (lane == 0) pn = atomicAdd(row_ctr, 1);
+                    const int rr = 2 * p + (lane >> 4);
+                    int e_rel = 0, deg = 0;
+                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = rp_s[rr + 1] - rp_s[rr]; }
+                    const bool hubrow = relay && deg > C::HUB_DEG;             // summed by the in-order relay below
+                    if (hubrow) deg = 0;
+                    const bool ok = rr < nrows && !hubrow;
+                    const int over = (e_rel + deg > C::CAP) ? 1 : 0;
+                    constexpr int MAXR = 12;
+                    float4 acc;
+                    if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
+                        acc = gather_smem_zm<MAXR>(lane_base, m.colidx + ebase + e_rel, deg, zrow, pol_keep);
+                    else
+                        acc = gather_smem_zm<MAXR>(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
+                    finish_row(rr, ok, acc);
+                    p = static_rows ? pn : __shfl_sync(0xffffffffu, pn, 0);
+                }
+                // Hub rows: loads by the whole pipeline (256 neighbours per round trip), adds relayed from warp to warp in
+                // column order through shared memory -- bitwise the serial walk (see step_dual_kernel / DESIGN.md 3.1)
+                if (relay) {
+                    HSYNC();                                             // every ordinary row is done; the colidx slice is dead
+                    volatile float* run = reinterpret_cast<volatile float*>(ci_s);          // [64] running sum
+                    uint64_t* hbar = reinterpret_cast<uint64_t*>(ci_s + H);                  // one mbarrier per warp: "your turn"
+                    if (t < PT / 32) umma::mbar_init(&hbar[t], 1);
+                    HSYNC();
+                    constexpr int SR = (PT / 16) * 8;                    // neighbours per super-round
+                    int nsr_done = 0;
+#pragma unroll 1
+                    for (int w = 0; w < TR / 32; ++w) {
+                        unsigned mm = hub_mask[w];
+                        while (mm) {
+                            const int r = 32 * w + __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const int dg = rp_s[r + 1] - rp_s[r];
+                            const int* cp = m.colidx + rp_s[r];
+                            const int n_sr = (dg + SR - 1) / SR;
+#pragma unroll 1
+                            for (int sr = 0; sr < n_sr; ++sr) {
+                                const int j0 = sr * SR + hw * 8;
+                                float4 v[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int c = (j0 + k < dg) ? cp[j0 + k] : zrow;
+                                    v[k] = ldg4_hint(lane_base + (size_t)(unsigned)c * H, pol_keep);
+                                }
+                                if (warp > 0) umma::mbar_wait(&hbar[warp], (uint32_t)(nsr_done & 1));
+                                else if (nsr_done > 0) umma::mbar_wait(&hbar[0], (uint32_t)((nsr_done - 1) & 1));
+                                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (!(sr == 0 && warp == 0)) {
+                                    sum.x = run[4 * l + 0]; sum.y = run[4 * l + 1]; sum.z = run[4 * l + 2]; sum.w = run[4 * l + 3];
+                                }
+                                if (lane < 16) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                }
+                                sum.x = __shfl_sync(0xffffffffu, sum.x, l); sum.y = __shfl_sync(0xffffffffu, sum.y, l);
+                                sum.z = __shfl_sync(0xffffffffu, sum.z, l); sum.w = __shfl_sync(0xffffffffu, sum.w, l);
+                                if (lane >= 16) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                    run[4 * l + 0] = sum.x; run[4 * l + 1] = sum.y; run[4 * l + 2] = sum.z; run[4 * l + 3] = sum.w;
+                                }
+                                __syncwarp();
+                                if (sr == n_sr - 1 && warp == PT / 32 - 1) {     // the row's sum is complete in the upper half-warp
+                                    const bool ok = lane >= 16;
+                                    finish_row(r, ok, sum);
+                                }
+                                if (lane == 0) umma::mbar_arrive(&hbar[(warp + 1) & (PT / 32 - 1)]);   // release: orders the stores above
+                                ++nsr_done;
+                            }
+                        }
+                    }
+                    HSYNC();
+                    if (t < PT / 32) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(&hbar[t])) : "memory");
+                }
+            } else {                                         // tile spans several (small) instances
+                int inst = m.inst0;
+#pragma unroll 1
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = hw + RSTEP * it;
+                    int row0 = 0, e0 = 0, deg = 0;
+                    const int32_t* ci = nullptr;
+                    if (rr < nrows) {
+                        const int g = tile0 + rr;
+                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
+                        const GnInstance I = a.bv.inst[inst];
+                        row0 = I.row0; ci = I.colidx;
+                        e0 = I.rowptr[g - row0];
+                        deg = I.rowptr[g - row0 + 1] - e0;
+                    }
+                    const float4 acc = gather_row(STP(ip_in), ci, e0, deg, row0, l, lane);
+                    finish_row(rr, rr < nrows, acc);
+                }
+            }
+        }
+        {
+            HSYNC();                                                            // S2b: every AI * S' row is parked
+            // ---- P3b: SIR update (own I_k / I'_k rows one pass ahead in registers; S_k from the raw operand tile; the
+            //      lane's 4 x 4 linear3 weights stay in registers for the four passes)
+            const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),
+                         w32 = lds4((const unsigned char*)W3s, 512 + 16 * l), w33 = lds4((const unsigned char*)W3s, 768 + 16 * l);
+            float4 iv, rv, ipo;
+            load_own(hw, hw < nrows, iv, rv, ipo);
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                const int rr = hw + RSTEP * it;
+                const bool ok = rr < nrows;
+                float hv[4];
+                update_row(rr, ok, lds4(Ls, off0 + it * PASS), iv, rv, ipo, w30, w31, w32, w33, hv);
+                if (it + 1 < 4) load_own(rr + RSTEP, rr + RSTEP < nrows, iv, rv, ipo);
+                hid_bfly(rr, ok, hv);
+            }
+        }
+        float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
+        float4 hRg = hI;                                 // RF: hid(R_k) of row t
+        if (STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
+        if (RF && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
+        umma::fence_proxy_async();
+        HSYNC();                                                                // S3 (every thread has read its copy of *meta)
+        // ---- P4: GEMM2 || metadata of the next tile || softmax of the input state ; I' epilogue (+ hid(I_{k+1}))
+        if (t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (t == PT - 32) fetch_meta(kfetch);
+        ++kfetch;
+        if (RF && t < nrows) {
+            const float4 c = *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            const float g = __fmul_rn(dt, bg_s[TR + t]);
+            *reinterpret_cast<float4*>(a.hid_r + (size_t)(tile0 + t) * 4) =
+                make_float4(fmaf(g, c.x, hRg.x), fmaf(g, c.y, hRg.y), fmaf(g, c.z, hRg.z), fmaf(g, c.w, hRg.w));
+        }
+        if (STP(probs) != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
+            const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
+            const float4 hR = RF ? hRg : *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            const float4 b3v = *reinterpret_cast<const float4*>(small);
+            const float4 w2v = *reinterpret_cast<const float4*>(small + 4);
+            const float b2v = small[8];
+#define GN_DEC(h) fmaf(w2v.w, fmaxf(h.w + b3v.w, 0.f), fmaf(w2v.z, fmaxf(h.z + b3v.z, 0.f), fmaf(w2v.y, fmaxf(h.y + b3v.y, 0.f), fmaf(w2v.x, fmaxf(h.x + b3v.x, 0.f), b2v))))
+            const float oS = GN_DEC(hS), oI = GN_DEC(hI), oR = GN_DEC(hR);
+#undef GN_DEC
+            const float mx = fmaxf(oS, fmaxf(oI, oR));
+            const float eS = ex2_approx((oS - mx) * 1.4426950408889634f), eI = ex2_approx((oI - mx) * 1.4426950408889634f),
+                        eR = ex2_approx((oR - mx) * 1.4426950408889634f);
+            const float inv = rcp_approx(eS + eI + eR);
+            float* pr = STP(probs) + (size_t)(tile0 + t) * 3;
+            pr[0] = eS * inv; pr[1] = eI * inv; pr[2] = eR * inv;
+        }
+        umma::mbar_wait_suspend(mbar, phase); phase ^= 1;
+        umma::fence_after_sync();
+        if (t == PT - 32) issue_s_load();                // GEMM2 has read Xs: the next tile's S_k rows may land there
+        {
+            float v[16];
+            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+                float4 o;
+                o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
+                o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
+                sts4(Ls, C::sw(erow, 4 * cq + j), o);
+            }
+            if (cq == 0) {
+                float hv[4];
+                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                if (erow < nrows) *reinterpret_cast<float4*>(a.hid_i + (size_t)(tile0 + erow) * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            }
+        }
+        umma::fence_before_sync();
+        umma::fence_proxy_async();                       // the staged tile is read by the TMA (async proxy)
+        HSYNC();                                                                // S4 (the next tile's metadata is published)
+        // ---- P5: I'_{k+1} tile -> HBM by two TMA tensor stores (rows past M are clipped by the tensor bounds)
+        if (t == 0) {
+            tma_store_2d(STP_TM(), Ls, 0, tile0, pol_stream);
+            tma_store_2d(STP_TM(), Ls + C::KBLK, 32, tile0, pol_stream);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        HSYNC();                                                                // S5
+    }
+    if (step + 1 < n_steps) {
+        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+    }
+    }
+#undef HSYNC
+#undef STP
+#undef STP_TM
+#undef STP_TMS
+#undef STP_SROW0
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(*tslot, C::TMEM_COLS);
+}
+
+}  // namespace gnode

@@ -50,12 +50,27 @@ def prediction_at_unit_times(S, I, R, maxTime, deltaT):
     return torch.stack(cols, dim=-1).transpose(0, 1)
 
 
-def l1_on_rollout(model, criterion, x, y, maxTime, deltaT):
-    """Forward + L1 loss on t >= 1 (t = 0 is the given initial condition). Returns (loss, n_items)."""
+def l1_on_rollout(model, criterion, x, y, maxTime, deltaT, instances=None, grad_scale=1.0):
+    """Forward + L1 loss on t >= 1 (t = 0 is the given initial condition). Returns (loss, n_items).
+
+    N1: with the drop-in modules, float64 labels and the reference's criterion (nn.L1Loss, mean) the rollout decodes and
+    stores ONLY the unit-time grid points int(i/deltaT) (what get_sir_t_nodes_torch would copy out, ode_nn.py:249-261),
+    and one kernel computes the float64 loss and the sparse cotangent dL/dprobs that the reverse sweep reads
+    (gn_ode_sir_b200.rollout.l1_subsampled). Anything else takes the generic torch path below."""
+    from . import rollout as _ro
+    steps = _ro.unit_time_steps(maxTime, deltaT)
+    fused = (hasattr(model, "rollout_probs") and isinstance(criterion, nn.L1Loss) and criterion.reduction == "mean"
+             and y.dtype == torch.float64 and x.is_cuda and len(steps) > 1 and bool(np.all(np.diff(steps) > 0)))
+    if fused:
+        kw = {"instances": instances} if instances is not None else {}
+        probs = model.rollout_probs(x, out_steps=steps, **kw)                    # [maxTime, M, 3]
+        target = y.reshape(-1, y.size(-2), y.size(-1))                          # [M, maxTime, 3] float64
+        loss = _ro.l1_subsampled(probs, target, skip=1, scale=grad_scale)
+        return loss, 3 * (probs.size(0) - 1) * probs.size(1)
     S, I, R = model(x)
     pred = prediction_at_unit_times(S, I, R, maxTime, deltaT)
     target = y.reshape(-1, y.size(-2), y.size(-1))
-    loss = criterion(pred[:, 1:, :], target[:, 1:, :].to(pred.dtype))
+    loss = criterion(pred[:, 1:, :], target[:, 1:, :])        # float64 labels promote the loss, as in the reference
     return loss, 3 * (pred.size(1) - 1) * pred.size(0)
 
 

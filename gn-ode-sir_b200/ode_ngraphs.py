@@ -16,8 +16,8 @@ from .graph import BatchCache, DeviceGraph
 class ODEfunc(nn.Module):
     def __init__(self, A_list, hidden1, device):
         super().__init__()
-        if hidden1 != _ro.H:
-            raise NotImplementedError("the B200 kernels are specialised for hidden width %d (got %d)" % (_ro.H, hidden1))
+        _ro.check_hidden(hidden1, need_marker=True)
+        self.hidden1 = hidden1
         self.A_list = A_list
         self.ln = nn.LayerNorm(hidden1)
         self.linear = nn.Linear(hidden1, hidden1)
@@ -25,15 +25,34 @@ class ODEfunc(nn.Module):
         self.sigmoid = nn.Sigmoid()
         self._graphs = None
         self._batches = BatchCache()
+        self._marker_cache = {}
 
     def device_graphs(self):
         if self._graphs is None:
             self._graphs = [DeviceGraph(A) for A in self.A_list]
         return self._graphs
 
+    def batch_from_instances(self, graph_ids):
+        """Batch of the instances graph_ids[i] (0-based indices into A_list): no device read."""
+        graphs = self.device_graphs()
+        return self._batches.get([graphs[int(g)] for g in graph_ids])
+
     def batch_from_markers(self, marker_col):
-        """marker_col: x[:, 5] (device or host). Non-zero entries open an instance."""
-        mk = marker_col.detach().to("cpu", torch.float32).numpy()
+        """marker_col: x[:, 5] (device or host). Non-zero entries open an instance. A device column costs one
+        device -> host copy (a stream sync): the result is remembered per (storage, version) of the input tensor, so a
+        loader batch that stays on the device resolves its instances once, not once per forward (the reference's
+        torch.nonzero(x[3,:,2]) at ode_nn_ngraphs.py:55 runs at every Euler step)."""
+        key = (marker_col.data_ptr(), marker_col.numel(), marker_col.stride(0), marker_col._version, str(marker_col.device))
+        hit = self._marker_cache.get(key)
+        if hit is not None:
+            return hit
+        batch = self._batch_from_marker_values(marker_col.detach().to("cpu", torch.float32).numpy())
+        if len(self._marker_cache) >= 256:
+            self._marker_cache.clear()
+        self._marker_cache[key] = batch
+        return batch
+
+    def _batch_from_marker_values(self, mk):
         starts = np.flatnonzero(mk)
         gids = mk[starts].astype(np.int64) - 1
         graphs = self.device_graphs()
@@ -48,8 +67,9 @@ class ODEfunc(nn.Module):
     def forward(self, t, x):
         """f(t, y) on the stacked state [4, sum N, H] (ode_nn_ngraphs.py:54-83); inference-only."""
         batch = self.batch_from_markers(x[3, :, 2])
-        dy = _ro.odefunc_eval(x[:3], x[3, :, 0], x[3, :, 1], batch,
-                              [self.linear.weight, self.linear.bias] + [self.linear.bias] * 6)
+        h = x.size(2)
+        W, b = _ro.pad_linear(self.linear.weight, self.linear.bias)
+        dy = _ro.odefunc_eval(_ro.pad_channels(x[:3]), x[3, :, 0], x[3, :, 1], batch, [W, b] + [b] * 6)[..., :h]
         return torch.cat((dy, torch.zeros_like(x[3:])))
 
 
@@ -74,13 +94,32 @@ class ODEBlock(nn.Module):
         self._dt = _ro.dt_array(self.integration_time)
 
     def _params(self):
-        return [self.odefunc.linear.weight, self.odefunc.linear.bias, self.linearS1.weight, self.linearS1.bias,
-                self.linear3.weight, self.linear3.bias, self.linearS2.weight, self.linearS2.bias]
+        return _ro.padded_params(self.odefunc.linear.weight, self.odefunc.linear.bias, self.linearS1.weight,
+                                 self.linearS1.bias, self.linear3.weight, self.linear3.bias, self.linearS2.weight,
+                                 self.linearS2.bias)
 
-    def forward(self, x):
-        batch = self.odefunc.batch_from_markers(x[:, 5])
-        probs = _ro.rollout(x, batch, self._dt, self._params(), self.grad_mode)
+    def _finish(self, probs):
         if probs.requires_grad:
             probs = probs + 0.0 * (self.odefunc.ln.weight.sum() + self.odefunc.ln.bias.sum())
-        S, I, R = probs.chunk(3, dim=-1)
+        return probs
+
+    def rollout_probs(self, x, out_steps=None, instances=None):
+        """x [sum N, 3+H] -> probabilities [T (or len(out_steps)), sum N, 3]. `instances` (graph index per instance)
+        spares the marker column's device read when the caller knows its batch."""
+        batch = self.odefunc.batch_from_instances(instances) if instances is not None \
+            else self.odefunc.batch_from_markers(x[:, 5])
+        if batch.M != x.size(0):
+            raise RuntimeError("batch of %d rows for an input of %d rows" % (batch.M, x.size(0)))
+        return self._finish(_ro.rollout(x, batch, self._dt, self._params(), self.grad_mode, out_steps))
+
+    def forward(self, x, instances=None):
+        S, I, R = self.rollout_probs(x, instances=instances).chunk(3, dim=-1)
         return S, I, R
+
+    def forward_trials(self, instances, seeds, beta, gamma, out_steps=None):
+        """Rollout from compact descriptors (N4): instance i runs on graph instances[i] with seeds[i], beta[i], gamma[i]
+        (replaces the dense per-instance blocks of ode_nn_ngraphs.py:326-345). Returns (S, I, R)."""
+        batch = self.odefunc.batch_from_instances(instances)
+        trials = _ro.TrialSet(seeds, beta, gamma, batch.sizes, self.linearS1.weight.device)
+        probs = self._finish(_ro.rollout_trials(batch, trials, self._dt, self._params(), self.grad_mode, out_steps))
+        return probs.chunk(3, dim=-1)

@@ -19,8 +19,8 @@ class ODEfunc(nn.Module):
 
     def __init__(self, A, beta, gamma, hidden1, device):
         super().__init__()
-        if hidden1 != _ro.H:
-            raise NotImplementedError("the B200 kernels are specialised for hidden width %d (got %d)" % (_ro.H, hidden1))
+        _ro.check_hidden(hidden1)
+        self.hidden1 = hidden1
         self.A = A
         self.beta = beta
         self.gamma = gamma
@@ -50,11 +50,12 @@ class ODEfunc(nn.Module):
         M = x.size(0) // 4
         N = self.device_graph().n
         batch = self.batch_for(M // N)
-        y = x[:3 * M].view(3, M, x.size(1))
+        h = x.size(1)
+        y = x[:3 * M].view(3, M, h)
         bg = x[3 * M:]
-        dy = _ro.odefunc_eval(y, bg[:, 0], bg[:, 1], batch,
-                              [self.linear.weight, self.linear.bias] + [self.linear.bias] * 6)
-        return torch.cat((dy.view(3 * M, -1), torch.zeros_like(bg)))
+        W, b = _ro.pad_linear(self.linear.weight, self.linear.bias)
+        dy = _ro.odefunc_eval(_ro.pad_channels(y), bg[:, 0], bg[:, 1], batch, [W, b] + [b] * 6)[..., :h]
+        return torch.cat((dy.reshape(3 * M, -1), torch.zeros_like(bg)))
 
 
 class ODEBlock(nn.Module):
@@ -83,17 +84,35 @@ class ODEBlock(nn.Module):
         self._dt = _ro.dt_array(self.integration_time)
 
     def _params(self):
-        return [self.odefunc.linear.weight, self.odefunc.linear.bias, self.linearS1.weight, self.linearS1.bias,
-                self.linear3.weight, self.linear3.bias, self.linearS2.weight, self.linearS2.bias]
+        return _ro.padded_params(self.odefunc.linear.weight, self.odefunc.linear.bias, self.linearS1.weight,
+                                 self.linearS1.bias, self.linear3.weight, self.linear3.bias, self.linearS2.weight,
+                                 self.linearS2.bias)
 
-    def forward(self, x):
-        x = x.view(-1, x.size(2))                      # [B*N, 3+H]
-        n_trials = x.size(0) // self.odefunc.device_graph().n
-        batch = self.odefunc.batch_for(n_trials)
-        probs = _ro.rollout(x, batch, self._dt, self._params(), self.grad_mode)   # [T, M, 3]
+    def _finish(self, probs):
         # adjoint parameters that never enter f get ZERO gradients in the reference (torchdiffeq
         # returns zeros for unused adjoint params): keep Adam's view of odefunc.ln identical
         if probs.requires_grad:
             probs = probs + 0.0 * (self.odefunc.ln.weight.sum() + self.odefunc.ln.bias.sum())
-        S, I, R = probs.chunk(3, dim=-1)               # each [T, M, 1]
+        return probs
+
+    def rollout_probs(self, x, out_steps=None):
+        """x [B, N, 3+H] -> probabilities [T (or len(out_steps)), B*N, 3] in one tensor."""
+        x = x.view(-1, x.size(-1))                     # [B*N, 3+H]
+        n_trials = x.size(0) // self.odefunc.device_graph().n
+        batch = self.odefunc.batch_for(n_trials)
+        return self._finish(_ro.rollout(x, batch, self._dt, self._params(), self.grad_mode, out_steps))
+
+    def forward(self, x):
+        S, I, R = self.rollout_probs(x).chunk(3, dim=-1)               # each [T, M, 1]
         return S, I, R
+
+    def forward_trials(self, seeds, beta, gamma, out_steps=None, probs_out=None, workspace=None):
+        """The same rollout from compact trial descriptors (N4): seeds[i] = node ids infected at t = 0 in trial i,
+        beta[i], gamma[i] -- instead of the dense [N, 3+H] block per trial main() builds (ode_nn_ngraph_sim.py:371-390).
+        Returns (S, I, R), each [T (or len(out_steps)), B*N, 1]."""
+        batch = self.odefunc.batch_for(len(seeds))
+        dev = self.linearS1.weight.device
+        trials = seeds if isinstance(seeds, _ro.TrialSet) else _ro.TrialSet(seeds, beta, gamma, batch.sizes, dev)
+        probs = self._finish(_ro.rollout_trials(batch, trials, self._dt, self._params(), self.grad_mode, out_steps,
+                                                probs_out, workspace))
+        return probs.chunk(3, dim=-1)

@@ -76,10 +76,12 @@ int gnode_version(void);
  * bit 1 = MUFU ex2/rcp sigmoid (else expf + IEEE division). Default: env GNODE_VARIANT or the build default. */
 int gnode_set_variant(int variant);
 int gnode_get_variant(void);
-/* Structure of the tensor-core step kernel (variants with bit 0 set): 3 = pipelined (default: one 1024-thread CTA per
- * SM running two 128-row tile pipelines that share the weight operand; the decoder's hidden layer comes out of the
- * step's two GEMMs), 4 = the same kernel with four 64-row pipelines, 1 = phase-structured (two 512-thread CTAs per
- * SM), 2 = warp-specialised, 0 = generic. Default: env GNODE_STEP_KERNEL or 3. All produce the same trajectories
+/* Structure of the tensor-core step kernel (variants with bit 0 set): 5 = pipelined, S_k stream by TMA (default: one
+ * 1024-thread CTA per SM running two 128-row tile pipelines that share the weight operand; the S_k tile arrives by TMA
+ * tensor loads straight into the UMMA operand layout, the raw fp32 tile is the hi operand and S_k is read once; the
+ * decoder's hidden layer comes out of the step's two GEMMs), 3 = the same pipeline with LDG-fed operands (round 1),
+ * 4 = 3 with four 64-row pipelines, 1 = phase-structured (two 512-thread CTAs per SM), 2 = warp-specialised,
+ * 0 = generic. Default: env GNODE_STEP_KERNEL or 5. All produce the same trajectories
  * within the parity tolerance. */
 int gnode_set_step_kernel(int kernel);
 int gnode_get_step_kernel(void);
@@ -91,6 +93,11 @@ int gnode_get_step_kernel(void);
  * selects 0. Training (traj != NULL) always stores R. */
 int gnode_set_r_state(int hidden);
 int gnode_get_r_state(void);
+/* Rollout launch structure of the tensor-core step kernels: 1 = ONE cooperative launch runs all Euler steps with a grid
+ * barrier between them, 0 = one launch per step, -1 (default) = cooperative for batches of up to 32 tiles per SM.
+ * Env GNODE_PERSISTENT=0/1 sets the initial value. Process-wide, like the other switches here. */
+int gnode_set_persistent(int mode);
+int gnode_get_persistent(void);
 /* debug: per-phase SM-cycle sums of the step kernel collected while env GNODE_DBG has bit 7 set; resets them */
 int gnode_debug_phase_cycles(long long* out8);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
@@ -144,6 +151,34 @@ int gnode_rollout_forward(gnode_batch_t b, const float* x, int64_t ldx, const gn
                           int32_t T, const float* dt_host, float* traj, float* probs,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same rollout emitting only selected grid points: out_steps (HOST int32[n_out], strictly ascending indices in
+ * [0,T)) names the grid points whose probabilities are written, probs is [n_out,M,3]; NULL = all T (n_out ignored).
+ * This is get_sir_t_nodes_torch's selection x_rk[int(i/deltaT)] (ode_nn.py:249-261; callers
+ * ode_nn_ngraph_sim.py:230-232,259-261,285-287) moved into the rollout: the decoder + softmax of the other grid points
+ * is never computed and never stored. */
+int gnode_rollout_forward_sel(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                              int32_t T, const float* dt_host, const int32_t* out_steps, int32_t n_out,
+                              float* traj, float* probs, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- N4: compact trial descriptors ------------------------------------------
+ * Replaces the dense [N, 3+H] fp32 input block per trial that main() builds on the host and ships to the device
+ * (ode_nn_ngraph_sim.py:371-390: I0[seeds] = 1, S0 = 1 - I0, R0 = 0, bg[:,0] = beta, bg[:,1] = gamma;
+ * ode_nn_ngraphs.py:326-345) and ODEBlock.forward unpacks again (:149-150). Instance i of the batch is described by
+ *   seeds[seed_ptr[i] .. seed_ptr[i+1])  instance-local node ids infected at t = 0 (DEVICE int32; seed_ptr[n_inst+1];
+ *                                        ids outside [0, n_i) are ignored)
+ *   beta[i], gamma[i]                    DEVICE fp32, one per instance.
+ * gnode_expand_trials writes the five live columns {S0, I0, R0, beta, gamma} of every row into x [M, ldx] (ldx >= 5;
+ * the remaining columns are not touched) -- the training path keeps that compact x for the reverse sweep.
+ * gnode_rollout_forward_trials = expansion (ldx = GNODE_TRIAL_LDX, in the workspace) + gnode_rollout_forward_sel. */
+#define GNODE_TRIAL_LDX 8
+int gnode_expand_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr, const float* beta,
+                        const float* gamma, float* x, int64_t ldx, void* stream);
+size_t gnode_rollout_trials_workspace_bytes(gnode_batch_t b, int with_traj);
+int gnode_rollout_forward_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr, const float* beta,
+                                 const float* gamma, const gnode_params_t* p, int32_t T, const float* dt_host,
+                                 const int32_t* out_steps, int32_t n_out, float* traj, float* probs,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a10: backward (reverse sweep over the stored trajectory) --------------
  * Replaces torchdiffeq OdeintAdjointMethod.backward + autograd of the encoder /
  * decoder (entered from loss.backward(), ode_nn_ngraph_sim.py:245).
@@ -154,6 +189,28 @@ int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t ldx, const g
                            int32_t T, const float* dt_host, const float* traj,
                            const float* grad_probs, int32_t grad_mode, float* grads_out,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same with a sparse cotangent: grad_probs is [n_out,M,3] for the grid points out_steps (as in
+ * gnode_rollout_forward_sel); grid points without a cotangent skip the decoder's backward, and reverse steps beyond the
+ * last selected grid point (zero adjoint) are not run. NULL = dense [T,M,3]. */
+int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                               int32_t T, const float* dt_host, const float* traj, const float* grad_probs,
+                               const int32_t* out_steps, int32_t n_out, int32_t grad_mode, float* grads_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- N1: L1 loss on the sub-sampled prediction and its cotangent, fused -------
+ * Replaces, per mini-batch, get_sir_t_nodes_torch x3 (60 row copies device -> CPU tensor, ode_nn.py:257-259), the
+ * cat / transpose / .to(device) and nn.L1Loss on [:,1:,:] (ode_nn_ngraph_sim.py:230-234, ode_nn_ngraphs.py:216-220),
+ * and the autograd of all of it: with probs [n_out,M,3] (fp32, the selected grid points, time-major as the rollout
+ * writes them) and labels [M,n_out,3] (fp64, node-major as the reference's y.view(-1, maxTime, 3)),
+ *   loss = mean over m, t >= skip, c of |probs[t,m,c] - labels[m,t,c]|      (float64 accumulation, like the reference's
+ *                                                                            promoted L1Loss)
+ *   grad_probs[t,m,c] = sign(probs - labels) * scale / count  for t >= skip, 0 for t < skip;  count = M (n_out-skip) 3.
+ * loss_out: DEVICE double[1]; grad_probs may be NULL (evaluation). scratch: gnode_l1_scratch_bytes() bytes. The sum is
+ * taken in a fixed order (per-block partial sums, then one block): bitwise reproducible. */
+size_t gnode_l1_scratch_bytes(void);
+int gnode_l1_loss_grad(const float* probs, const double* labels, int64_t M, int32_t n_out, int32_t skip, float scale,
+                       double* loss_out, float* grad_probs, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

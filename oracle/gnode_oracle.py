@@ -203,9 +203,32 @@ def loss_and_grads(x, params, coo, t, weight, grad_mode="adjoint"):
         raise ValueError(grad_mode)
     probs = decode(traj[:, 0], traj[:, 1], traj[:, 2], p["linear3.weight"], p["linear3.bias"],
                    p["linearS2.weight"], p["linearS2.bias"])
-    loss = (probs * weight).sum()
+    loss = weight(probs) if callable(weight) else (probs * weight).sum()
     loss.backward()
     return loss.detach(), {k: p[k].grad.detach().clone() for k in GRAD_KEYS}
+
+
+def unit_time_rows(maxTime, deltaT):
+    """Rows get_sir_t_nodes_torch copies out of a [T, nodes] trajectory: int(i/deltaT), i = 0..maxTime-1
+    (/root/reference/ode_nn.py:249-261, count=False branch)."""
+    return [int(i / deltaT) for i in range(int(maxTime))]
+
+
+def train_loss(probs, y, maxTime, deltaT):
+    """The loss of the reference's train()/test() (/root/reference/ode_nn_ngraph_sim.py:230-234,
+    ode_nn_ngraphs.py:212-216): the S, I, R predictions at the unit-time rows, stacked on the last axis and
+    transposed to [M, maxTime, 3], against the labels y.view(-1, maxTime, 3) (float64), nn.L1Loss (mean) on
+    [:, 1:, :]. The float32 prediction is promoted to float64 by the subtraction, as in the reference."""
+    rows = torch.tensor(unit_time_rows(maxTime, deltaT))
+    pred = probs.index_select(0, rows).transpose(0, 1)                    # [M, maxTime, 3]
+    target = y.reshape(-1, y.size(-2), y.size(-1))
+    return torch.nn.functional.l1_loss(pred[:, 1:, :], target[:, 1:, :]) if pred.dtype == target.dtype \
+        else (pred[:, 1:, :] - target[:, 1:, :]).abs().mean()
+
+
+def train_loss_and_grads(x, params, coo, t, y, maxTime, deltaT, grad_mode="adjoint"):
+    """One train() mini-batch of the reference: (loss, {key: grad})."""
+    return loss_and_grads(x, params, coo, t, lambda probs: train_loss(probs, y, maxTime, deltaT), grad_mode)
 
 
 # --------------------------------------------------------------------------

@@ -8,6 +8,11 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+# On the larger graphs the reference's own fp32 run is not reproducible to 1e-5 (hidden states grow to ~1e3, SURVEY H1:
+# its fp32-vs-fp64 difference is 4e-5 (ng_train5) .. 2e-3 (wiki-vote), and its wiki-vote fp32 GRADIENT differs from the
+# fp64 one by ~100 %): those cases are judged against the float64 run, err(ours) <= max(bar, 2 * err(reference fp32)).
+LARGE_CASES = [c for c in GOLDEN_CASES if any(k in c for k in ("fbsocial", "openflights", "wikivote", "train5"))]
+STRICT_CASES = [c for c in GOLDEN_CASES if c not in LARGE_CASES]
 
 
 class Golden:

@@ -9,6 +9,7 @@ to outputs of ``ODEfunc``/``ODEBlock`` from
 on seeded weights and inputs.
 
     python tests/golden/make_golden.py          # rewrites every fixture
+    python tests/golden/make_golden.py NAME...  # only the named cases
 
 Each npz holds: CSR of every graph used (indptr/indices int32), the instance ->
 graph map, x [M,3+H] fp32, the full state_dict, the reference outputs
@@ -39,6 +40,12 @@ CASES = [
     ("sim_fbfood_b2", "sim", ["fb-food"], [0] * 2, 3, True, 1),
     ("sim_fbsocial_b1", "sim", ["fb-social"], [0], 4, False, 3),
     ("ng_mixed_b5", "ngraphs", ["karate", "dolphins", "fb-food"], [0, 1, 0, 2, 1], 5, True, 1),
+    # power-law graphs of BASELINE configs[2]/[3]: wiki-vote (max degree 1065: hub rows, CSR-slice overflow),
+    # openflights, and a multi-graph training batch over the five training graphs (ode_nn_ngraphs.py:311-312)
+    ("sim_openflights_b2", "sim", ["openflights"], [0] * 2, 7, True, 4),
+    ("sim_wikivote_b2", "sim", ["wiki-vote"], [0] * 2, 6, True, 4),
+    ("ng_train5_b8", "ngraphs", ["dolphins", "fb-food", "fb-social", "openflights", "wiki-vote"],
+     [0, 1, 2, 3, 4, 0, 1, 2], 8, True, 4),
 ]
 
 
@@ -78,7 +85,10 @@ def grads_of(blk):
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, variant, gnames, inst_graph, seed, with_grads, tstride in CASES:
+        if only and name not in only:
+            continue
         adjs = [rh.load_reference_graph(g) for g in gnames]
         blocks = make_x(variant, adjs, inst_graph, seed)
         out = {"variant": variant, "graph_names": np.array(gnames), "inst_graph": np.array(inst_graph, np.int32),

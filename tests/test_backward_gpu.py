@@ -7,12 +7,12 @@ between implementations; 2e-4 * max|grad| per tensor (the oracle's own fp32-vs-r
 import pytest
 import torch
 
-from _util import GOLDEN_CASES, Golden
+from _util import LARGE_CASES, STRICT_CASES, Golden
 from oracle import gnode_oracle as orc
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-GRAD_CASES = [c for c in GOLDEN_CASES if "fbsocial" not in c]
+GRAD_CASES = STRICT_CASES
 
 
 @pytest.fixture(scope="module")
@@ -64,6 +64,61 @@ def test_gradients_match_reference(gn, name, mode):
         assert float(got["odefunc.ln.weight"].abs().max()) == 0.0
         assert float(got["odefunc.ln.bias"].abs().max()) == 0.0
     assert blk.ln.weight.grad is None
+
+
+@pytest.mark.parametrize("mode", ["adjoint", "discrete"])
+@pytest.mark.parametrize("name", [c for c in LARGE_CASES if Golden(c).has_grads])
+def test_gradients_large_graphs_against_fp64(gn, name, mode):
+    """openflights, wiki-vote (hub rows in the A^T gather of bwd_gz_kernel, ragged tiles at scale) and the five-graph
+    training batch. The reference's own fp32 gradients are 2e-3 (train5) .. ~1 (wiki-vote, scale-relative) away from its
+    float64 gradients on these graphs, so the yardstick is the float64 gradient with the reference's fp32 error as bar."""
+    g = Golden(name)
+    blk, probs = cuda_grads(gn, g, mode)
+    got = {k: p.grad.detach().cpu() for k, p in blk.named_parameters() if p.grad is not None}
+    for k in orc.GRAD_KEYS:
+        ref32, ref64 = g.grads[("g32", mode)][k], g.grads[("g64", mode)][k]
+        scale = max(ref64.abs().max().item(), 1.0)
+        e_ref = (ref32.double() - ref64).abs().max().item() / scale
+        e64 = (got[k].double() - ref64).abs().max().item() / scale
+        print("%s %s %s: ours %.3e reference fp32 %.3e" % (name, mode, k, e64, e_ref))
+        # (wiki-vote: the reference's own fp32 gradient is 20 .. 100 % away from its float64 one -- rounding noise
+        # amplified by the dynamics -- so this only says "same order of noise"; the sharp checks on that graph are the
+        # short-horizon test below and the per-kernel aggregation / teacher-forced tests)
+        assert e64 <= max(1e-3, 4.0 * e_ref), (k, e64, e_ref)
+
+
+@pytest.mark.parametrize("mode", ["adjoint", "discrete"])
+def test_gradients_wikivote_short_horizon(gn, mode):
+    """wiki-vote (max degree 1065) with a 6-point grid: the reverse sweep's A^T hub gather, decoder and weight-gradient
+    reductions against the CPU oracle in float64. Even at this horizon the fp32 oracle (= the reference's arithmetic) is
+    1.5e-3 .. 2.6e-3 scale-relative away from float64 on the [64,64] weight (sums over 14k rows with 1e3-term hub rows),
+    so the bar is max(1e-3, 2 x the fp32 oracle's own error), per tensor."""
+    g = Golden("sim_wikivote_b2")
+    A, N, B = g.adjs[0], g.adjs[0].shape[0], 2
+    x = g.x
+    t = orc.time_grid(3, 0.5)
+    w = torch.randn(len(t), B * N, 3, generator=torch.Generator().manual_seed(11))
+    coo = orc.batch_coo([A], [0] * B)
+    _, ref32 = orc.loss_and_grads(x, g.params, coo, t, w, mode)
+    torch.set_default_dtype(torch.float64)
+    try:
+        _, want = orc.loss_and_grads(x.double(), {k: v.double() for k, v in g.params.items()}, coo, t, w.double(), mode)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, DEV)
+    blk = gn.ode_sim.ODEBlock(3, 0.5, N, [0, 1], 64, of, DEV)
+    blk.load_state_dict(g.params)
+    blk.to(DEV)
+    blk.grad_mode = mode
+    S, I, R = blk(x.view(B, N, -1).to(DEV))
+    (torch.cat((S, I, R), -1) * w.to(DEV)).sum().backward()
+    for k in orc.GRAD_KEYS:
+        got = dict(blk.named_parameters())[k].grad.cpu().double()
+        scale = max(want[k].abs().max().item(), 1.0)
+        err = (got - want[k]).abs().max().item() / scale
+        e_ref = (ref32[k].double() - want[k]).abs().max().item() / scale
+        print("wiki-vote T=6 %s %s: ours %.3e, fp32 oracle %.3e" % (mode, k, err, e_ref))
+        assert err <= max(1e-3, 2.0 * e_ref), (mode, k, err, e_ref)
 
 
 def test_backward_is_deterministic(gn):

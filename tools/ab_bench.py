@@ -3,7 +3,7 @@ events): interleaves the configurations given on the command line and prints nod
 
     python tools/ab_bench.py [--trials 64] [--rounds 3] r_state=0 r_state=1 dbg=1048576 ...
 Each configuration is a comma-separated list of key=value: r_state (gnode_set_r_state), dbg (env GNODE_DBG, read per
-rollout), kernel (gnode_set_step_kernel)."""
+rollout), kernel (gnode_set_step_kernel), variant (gnode_set_variant: 0 = FFMA + expf, the reference's arithmetic)."""
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -49,7 +49,7 @@ x = x.to(dev)
 
 def apply(cfg):
     os.environ.pop("GNODE_DBG", None)
-    L.gnode_set_r_state(1); L.gnode_set_step_kernel(3)
+    L.gnode_set_r_state(1); L.gnode_set_step_kernel(5); L.gnode_set_variant(3)
     for kv in cfg.split(","):
         k, v = kv.split("=")
         if k == "r_state":
@@ -58,6 +58,8 @@ def apply(cfg):
             os.environ["GNODE_DBG"] = v
         elif k == "kernel":
             L.gnode_set_step_kernel(int(v))
+        elif k == "variant":
+            L.gnode_set_variant(int(v))
         elif k != "base":
             raise SystemExit("unknown key " + k)
 
