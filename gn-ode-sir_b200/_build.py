@@ -9,7 +9,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgnode_b200.so")
-SOURCES = ["gnode_graph.cu", "gnode_forward.cu", "gnode_backward.cu", "gnode_loss.cu"]
+SOURCES = ["gnode_graph.cu", "gnode_forward.cu", "gnode_backward.cu", "gnode_loss.cu", "gnode_mc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

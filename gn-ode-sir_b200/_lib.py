@@ -67,6 +67,9 @@ SIGNATURES = {
     "gnode_rollout_backward_sel": (c_int, [c_void_p, c_void_p, c_int64, ctypes.POINTER(GnodeParams), c_int32,
                                            c_float_p, c_void_p, c_void_p, c_int32_p, c_int32, c_int32, c_void_p,
                                            c_void_p, c_size_t, c_void_p]),
+    "gnode_mc_sir_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
+    "gnode_mc_sir": (c_int, [c_void_p, c_void_p, c_int32, ctypes.c_float, ctypes.c_float, c_int32, c_int32,
+                             ctypes.c_uint64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnode_l1_scratch_bytes": (c_size_t, []),
     "gnode_l1_loss_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, ctypes.c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),

@@ -1,6 +1,7 @@
 // Internal declarations shared by the kernels of libgnode_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -17,7 +18,7 @@ constexpr int CHUNKS = H / 4;         // 16-byte chunks per row (16)
 
 // ---- host side ------------------------------------------------------------
 void set_error(const char* fmt, ...);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;
 
 #define GN_CUDA(call)                                                              \
     do {                                                                           \

@@ -1778,23 +1778,23 @@ static int launch_step_dual(const gnode_batch* b, const StepArgs& a, cudaStream_
     return GNODE_OK;
 }
 
-template <bool FAST, bool RF>
+template <bool FAST, bool RF, int OPT>
 static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     static bool configured[64] = {false};
     if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, false, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
-        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, true, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, false, RF, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, true, RF, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
         configured[b->device & 63] = true;
     }
     const int grid = std::min(b->n_tiles, b->sm_count);
     if (a.n_steps > 0) {
         void* params[] = {const_cast<StepArgs*>(&a)};
-        GN_CUDA(cudaLaunchCooperativeKernel((const void*)step_stream_kernel<FAST, true, RF>, dim3(grid), dim3(D_THREADS), params,
+        GN_CUDA(cudaLaunchCooperativeKernel((const void*)step_stream_kernel<FAST, true, RF, OPT>, dim3(grid), dim3(D_THREADS), params,
                                             (size_t)StreamCfg::TOTAL, stream));
         gnode::g_launches++;
         return GNODE_OK;
     }
-    step_stream_kernel<FAST, false, RF><<<grid, D_THREADS, StreamCfg::TOTAL, stream>>>(a);
+    step_stream_kernel<FAST, false, RF, OPT><<<grid, D_THREADS, StreamCfg::TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;
 }
@@ -1803,7 +1803,7 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
 // kernel with 4 x 64-row pipelines, 1 = phase-structured, 2 = warp-specialised, 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 5) : 5; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 9) : 5; }
     return g_step_kernel;
 }
 
@@ -1840,10 +1840,18 @@ template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
     if (MODE == MODE_STEP && use_dual()) {
-        if (step_kernel_choice() >= 5 && a.use_tma == 2) {      // TMA-fed S stream
+        if (step_kernel_choice() >= 5 && a.use_tma == 2) {      // TMA-fed S stream; 6 / 7 / 8: ablations of its two overlaps
             const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
-            return fast ? (rf ? launch_step_stream<true, true>(b, a, stream) : launch_step_stream<true, false>(b, a, stream))
-                        : (rf ? launch_step_stream<false, true>(b, a, stream) : launch_step_stream<false, false>(b, a, stream));
+#define GN_SS(O) (fast ? (rf ? launch_step_stream<true, true, O>(b, a, stream) : launch_step_stream<true, false, O>(b, a, stream)) \
+                       : (rf ? launch_step_stream<false, true, O>(b, a, stream) : launch_step_stream<false, false, O>(b, a, stream)))
+            switch (step_kernel_choice()) {
+                case 6: return GN_SS(0);
+                case 7: return GN_SS(1);
+                case 8: return GN_SS(2);
+                case 9: return GN_SS(7);
+                default: return GN_SS(3);
+            }
+#undef GN_SS
         }
         if (step_kernel_choice() == 4) return (var & VAR_FASTSIG) ? launch_step_dual<true, 4, false>(b, a, stream) : launch_step_dual<false, 4, false>(b, a, stream);
         if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
@@ -1904,7 +1912,7 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
-    if (kernel < 0 || kernel > 5) { set_error("gnode_set_step_kernel: kernel must be 0..5"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 9) { set_error("gnode_set_step_kernel: kernel must be 0..9"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }
@@ -2199,6 +2207,7 @@ extern "C" int gnode_odefunc_eval(gnode_batch_t b, const float* y, const float* 
         set_error("gnode_odefunc_eval: null argument");
         return GNODE_ERR_ARG;
     }
+    if (int rc = check_current_device(b, "gnode_odefunc_eval")) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     StepArgs a{};
     a.bv = gn_view(b);

@@ -1,5 +1,6 @@
 // Graph / batch handles and the standalone neighbour aggregation (a6, a7).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstdarg>
 #include <cstring>
@@ -9,7 +10,7 @@
 namespace gnode {
 
 static thread_local char t_err[1024] = "";
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -73,21 +74,23 @@ extern "C" int gnode_graph_create(int32_t n, int64_t nnz, const int32_t* rowptr,
                   (long long)nnz);
         return GNODE_ERR_ARG;
     }
+    // validate the whole CSR before touching it: a malformed rowptr must not drive the per-row sort out of bounds
+    for (int32_t r = 0; r < n; ++r)
+        if (rowptr[r + 1] < rowptr[r] || rowptr[r + 1] > nnz) {
+            set_error("gnode_graph_create: rowptr not monotone within [0, nnz] at row %d", r);
+            return GNODE_ERR_ARG;
+        }
+    for (int64_t e = 0; e < nnz; ++e)
+        if (colidx[e] < 0 || colidx[e] >= n) {
+            set_error("gnode_graph_create: column index %d out of range at entry %lld", colidx[e], (long long)e);
+            return GNODE_ERR_ARG;
+        }
     std::vector<int32_t> ci(colidx, colidx + nnz);
     int32_t maxdeg = 0;
     for (int32_t r = 0; r < n; ++r) {
-        if (rowptr[r + 1] < rowptr[r]) {
-            set_error("gnode_graph_create: rowptr not monotone at row %d", r);
-            return GNODE_ERR_ARG;
-        }
         std::sort(ci.begin() + rowptr[r], ci.begin() + rowptr[r + 1]);
         maxdeg = std::max(maxdeg, rowptr[r + 1] - rowptr[r]);
     }
-    for (int64_t e = 0; e < nnz; ++e)
-        if (ci[e] < 0 || ci[e] >= n) {
-            set_error("gnode_graph_create: column index %d out of range at entry %lld", ci[e], (long long)e);
-            return GNODE_ERR_ARG;
-        }
     // transpose pattern by counting sort (rows ascending -> columns of A^T ascending)
     std::vector<int32_t> rpt(n + 1, 0), cit(nnz);
     for (int64_t e = 0; e < nnz; ++e) rpt[ci[e] + 1]++;
@@ -103,6 +106,8 @@ extern "C" int gnode_graph_create(int32_t n, int64_t nnz, const int32_t* rowptr,
     gnode_graph* g = new gnode_graph();
     g->n = n; g->nnz = nnz; g->max_degree = maxdeg; g->symmetric = sym ? 1 : 0;
     g->h_rowptr.assign(rowptr, rowptr + n + 1);
+    // device side: any CUDA failure frees what was allocated so far together with the handle
+    auto upload = [&]() -> int {
     GN_CUDA(cudaGetDevice(&g->device));
     const size_t nnz_alloc = (size_t)std::max<int64_t>(nnz, 1);
     GN_CUDA(cudaMalloc(&g->d_rowptr, sizeof(int32_t) * (n + 1)));
@@ -117,6 +122,15 @@ extern "C" int gnode_graph_create(int32_t n, int64_t nnz, const int32_t* rowptr,
         GN_CUDA(cudaMalloc(&g->d_colidx_t, sizeof(int32_t) * nnz_alloc));
         GN_CUDA(cudaMemcpy(g->d_rowptr_t, rpt.data(), sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice));
         if (nnz) GN_CUDA(cudaMemcpy(g->d_colidx_t, cit.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+    }
+    return GNODE_OK;
+    };
+    const int rc = upload();
+    if (rc != GNODE_OK) {
+        if (g->d_rowptr_t == g->d_rowptr) { g->d_rowptr_t = nullptr; g->d_colidx_t = nullptr; }
+        g->symmetric = 0;                        // free whichever of the four arrays exist, once each
+        gnode_graph_destroy(g);
+        return rc;
     }
     *out = g;
     return GNODE_OK;
@@ -202,8 +216,18 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
         }
         flush();
     }
-    GN_CUDA(cudaGetDevice(&b->device));
-    GN_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
+    {
+        cudaError_t e = cudaGetDevice(&b->device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device);
+        if (e != cudaSuccess) { set_error("gnode_batch_create: %s", cudaGetErrorString(e)); delete b; return GNODE_ERR_CUDA; }
+        for (int32_t i = 0; i < n_inst; ++i)
+            if (inst_graphs[i]->device != b->device) {
+                set_error("gnode_batch_create: graph of instance %d lives on device %d, the current device is %d", i,
+                          inst_graphs[i]->device, b->device);
+                delete b;
+                return GNODE_ERR_ARG;
+            }
+    }
     // Tail control. A row is summed by ONE half-warp in rounds of 8 neighbours, strictly in ascending column order (the
     // order of the reference's CPU scatter_add_: hub sums of ~1e3 amplify any re-association to ~1e-3 in the hidden
     // state, so the row is not split across warps). A round costs ~2.4k cycles under load, i.e. a tile with a hub row of
@@ -231,6 +255,8 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
             order.swap(reordered);
         }
     }
+    // device side: any CUDA failure frees what was allocated so far together with the handle
+    auto upload = [&]() -> int {
     GN_CUDA(cudaMalloc(&b->d_inst, sizeof(GnInstance) * n_inst));
     GN_CUDA(cudaMalloc(&b->d_tile_inst, sizeof(int32_t) * b->n_tiles));
     GN_CUDA(cudaMalloc(&b->d_tile_order, sizeof(int32_t) * b->n_tiles));
@@ -286,6 +312,10 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
         GN_CUDA(cudaMalloc(&b->d_sub_meta, sizeof(int4) * sm.size()));
         GN_CUDA(cudaMemcpy(b->d_sub_meta, sm.data(), sizeof(int4) * sm.size(), cudaMemcpyHostToDevice));
     }
+    return GNODE_OK;
+    };
+    const int rc = upload();
+    if (rc != GNODE_OK) { gnode_batch_destroy(b); return rc; }
     *out = b;
     return GNODE_OK;
 }
@@ -306,6 +336,7 @@ extern "C" int64_t gnode_batch_rows(gnode_batch_t b) { return b ? b->M : -1; }
 
 extern "C" int gnode_aggregate(gnode_batch_t b, const float* in, float* out, int transpose, void* stream) {
     if (!b || !in || !out) { set_error("gnode_aggregate: null argument"); return GNODE_ERR_ARG; }
+    if (int rc = check_current_device(b, "gnode_aggregate")) return rc;
     const int hw_per_block = 256 / 16;
     int64_t blocks = (b->M + hw_per_block - 1) / hw_per_block;
     blocks = std::min<int64_t>(blocks, (int64_t)b->sm_count * 16);

@@ -99,7 +99,7 @@ struct SStep {
     float dt;
 };
 
-template <bool FAST, bool PERSIST, bool RF>
+template <bool FAST, bool PERSIST, bool RF, int OPT>      // OPT bit 0: first gather overlaps GEMM1, bit 1: first own-row loads cross the barrier
 __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_constant__ StepArgs a) {
     using C = StreamCfg;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
 
     umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
     if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
-    if (t == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(sbar, 1); }
+    if (t == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(sbar, (OPT & 4) ? 2 : 1); }
     umma::fence_before_sync();
     if (tid < H) bs[tid] = a.p.lin_b[tid];
     if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         fetch_meta(0);
         if (PERSIST) asm volatile("fence.proxy.async;" ::: "memory");   // state rows written by other SMs (generic proxy) -> TMA reads
         issue_s_load();
+        if ((OPT & 4) && meta->seq < n_tiles) umma::mbar_arrive(sbar);   // second arrival: Ls is free (no TMA store pending)
     }
     kfetch = 1;
     HSYNC();
@@ -264,6 +265,38 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         if (t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
         if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
+        // row pairs of the neighbour gather: strided over the warps when the tile's CSR slice fits the staged window,
+        // shared-memory tickets for hub tiles so that a long row does not leave the other warps idle
+        const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
+        const int zrow = M - i_row0;                         // the all-zero row that follows the I' rows
+        const bool static_rows = m.ecnt <= C::CAP;
+        int sj = 0;
+        auto draw_pair = [&]() -> int {
+            if (static_rows) { const int pp = warp + (PT / 32) * sj; ++sj; return pp; }
+            int pp = 0;
+            if (lane == 0) pp = atomicAdd(row_ctr, 1);
+            return __shfl_sync(0xffffffffu, pp, 0);
+        };
+        auto gather_pair = [&](int p, int& rr, bool& ok) -> float4 {
+            rr = 2 * p + (lane >> 4);
+            int e_rel = 0, deg = 0;
+            if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = rp_s[rr + 1] - rp_s[rr]; }
+            const bool hubrow = relay && deg > C::HUB_DEG;                 // summed by the in-order relay below
+            if (hubrow) deg = 0;
+            ok = rr < nrows && !hubrow;
+            const int over = (e_rel + deg > C::CAP) ? 1 : 0;
+            if (__any_sync(0xffffffffu, over))               // indices beyond the staged slice: same gather on the global list
+                return gather_smem_zm<12>(lane_base, m.colidx + ebase + e_rel, deg, zrow, pol_keep);
+            return gather_smem_zm<12>(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
+        };
+        // The gather needs nothing of GEMM1 (only folding AI into S' does): the first row pair's neighbour rows are
+        // fetched and summed WHILE the tensor core runs, which hides the GEMM and its completion latency behind one
+        // memory round trip (ordinary single-instance tiles; relay tiles first have to publish their hub mask)
+        const bool early = (OPT & 1) && single && !relay;
+        int p_e = 0, rr_e = 0;
+        bool ok_e = false;
+        float4 acc_e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (early) { p_e = draw_pair(); if (p_e < TR / 2) acc_e = gather_pair(p_e, rr_e, ok_e); }
         umma::mbar_wait_suspend(mbar, phase); phase ^= 1;
         umma::fence_after_sync();
         {
@@ -351,35 +384,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
 
         // ---- P3a: neighbour sums AI (sequential, ascending columns), folded into S' in place
         {
-            const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
-            const int zrow = M - i_row0;                     // the all-zero row that follows the I' rows
             if (single) {
-                const bool static_rows = m.ecnt <= C::CAP;
-                int p = 0, sj = 1;
-                if (static_rows) p = warp;
-                else {
-                    if (lane == 0) p = atomicAdd(row_ctr, 1);
-                    p = __shfl_sync(0xffffffffu, p, 0);
-                }
+                int p;
+                if (early) {
+                    if (p_e < TR / 2) finish_row(rr_e, ok_e, acc_e);
+                    p = p_e < TR / 2 ? draw_pair() : p_e;
+                } else p = draw_pair();
                 while (p < TR / 2) {
-                    int pn = 0;
-                    if (static_rows) { pn = warp + (PT / 32) * sj; ++sj; }
-                    else if (lane == 0) pn = atomicAdd(row_ctr, 1);
-                    const int rr = 2 * p + (lane >> 4);
-                    int e_rel = 0, deg = 0;
-                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = rp_s[rr + 1] - rp_s[rr]; }
-                    const bool hubrow = relay && deg > C::HUB_DEG;             // summed by the in-order relay below
-                    if (hubrow) deg = 0;
-                    const bool ok = rr < nrows && !hubrow;
-                    const int over = (e_rel + deg > C::CAP) ? 1 : 0;
-                    constexpr int MAXR = 12;
-                    float4 acc;
-                    if (__any_sync(0xffffffffu, over))           // indices beyond the staged slice: same gather on the global list
-                        acc = gather_smem_zm<MAXR>(lane_base, m.colidx + ebase + e_rel, deg, zrow, pol_keep);
-                    else
-                        acc = gather_smem_zm<MAXR>(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
+                    int rr; bool ok;
+                    const float4 acc = gather_pair(p, rr, ok);
                     finish_row(rr, ok, acc);
-                    p = static_rows ? pn : __shfl_sync(0xffffffffu, pn, 0);
+                    p = draw_pair();
                 }
                 // Hub rows: loads by the whole pipeline (256 neighbours per round trip), adds relayed from warp to warp in
                 // column order through shared memory -- bitwise the serial walk (see step_dual_kernel / DESIGN.md 3.1)
@@ -460,13 +475,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
         }
         {
+            // the own rows of the first pass are requested BEFORE the barrier: their latency overlaps the wait for the
+            // slowest gathering warp
+            float4 iv, rv, ipo;
+            if (OPT & 2) load_own(hw, hw < nrows, iv, rv, ipo);
             HSYNC();                                                            // S2b: every AI * S' row is parked
             // ---- P3b: SIR update (own I_k / I'_k rows one pass ahead in registers; S_k from the raw operand tile; the
             //      lane's 4 x 4 linear3 weights stay in registers for the four passes)
             const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),
                          w32 = lds4((const unsigned char*)W3s, 512 + 16 * l), w33 = lds4((const unsigned char*)W3s, 768 + 16 * l);
-            float4 iv, rv, ipo;
-            load_own(hw, hw < nrows, iv, rv, ipo);
+            if (!(OPT & 2)) load_own(hw, hw < nrows, iv, rv, ipo);
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
                 const int rr = hw + RSTEP * it;
@@ -538,8 +556,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             tma_store_2d(STP_TM(), Ls + C::KBLK, 32, tile0, pol_stream);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            // OPT bit 2: no block barrier here. The staged tile may be overwritten once the bulk group has read it; the next
+            // tile's threads learn that through the S-load mbarrier, whose second arrival is this thread's (they wait on
+            // it before their first write to Ls), so the store's read time overlaps the S load and the CSR staging.
+            if ((OPT & 4) && meta->seq < n_tiles) umma::mbar_arrive(sbar);
         }
-        HSYNC();                                                                // S5
+        if (!(OPT & 4)) HSYNC();                                                // S5
     }
     if (step + 1 < n_steps) {
         if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -110,9 +110,10 @@ class ODEBlock(nn.Module):
         """The same rollout from compact trial descriptors (N4): seeds[i] = node ids infected at t = 0 in trial i,
         beta[i], gamma[i] -- instead of the dense [N, 3+H] block per trial main() builds (ode_nn_ngraph_sim.py:371-390).
         Returns (S, I, R), each [T (or len(out_steps)), B*N, 1]."""
-        batch = self.odefunc.batch_for(len(seeds))
+        is_set = isinstance(seeds, _ro.TrialSet)                      # a prepared (device-resident) descriptor set
+        batch = self.odefunc.batch_for(seeds.n_inst if is_set else len(seeds))
         dev = self.linearS1.weight.device
-        trials = seeds if isinstance(seeds, _ro.TrialSet) else _ro.TrialSet(seeds, beta, gamma, batch.sizes, dev)
+        trials = seeds if is_set else _ro.TrialSet(seeds, beta, gamma, batch.sizes, dev)
         probs = self._finish(_ro.rollout_trials(batch, trials, self._dt, self._params(), self.grad_mode, out_steps,
                                                 probs_out, workspace))
         return probs.chunk(3, dim=-1)

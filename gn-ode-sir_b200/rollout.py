@@ -157,11 +157,12 @@ def rollout(x, batch, dt, params, grad_mode="adjoint", out_steps=None):
 
 
 class TrialSet:
-    """Compact trial descriptors of one batch on the device (N4): per instance the seed list (instance-local node
-    ids), beta and gamma -- what main() expands into a dense [N, 3+H] block per trial on the host
-    (ode_nn_ngraph_sim.py:371-390). A few KB per batch instead of 268 B per row."""
+    """Compact trial descriptors of one batch (N4): per instance the seed list (instance-local node ids), beta and
+    gamma -- what main() expands into a dense [N, 3+H] block per trial on the host (ode_nn_ngraph_sim.py:371-390).
+    A few KB per batch instead of 268 B per row. device=None keeps the set in pinned host memory (a dataset of
+    batches that a streaming loop copies into a device-resident set with copy_from)."""
 
-    def __init__(self, seeds, beta, gamma, sizes, device):
+    def __init__(self, seeds, beta, gamma, sizes, device=None):
         if not (len(seeds) == len(beta) == len(gamma) == len(sizes)):
             raise ValueError("seeds, beta, gamma and sizes must have one entry per instance")
         ptr = np.zeros(len(seeds) + 1, dtype=np.int32)
@@ -170,24 +171,40 @@ class TrialSet:
             sd = np.asarray(sd, dtype=np.int64).reshape(-1)
             if len(sd) and (sd.min() < 0 or sd.max() >= n):
                 raise ValueError("instance %d: seed %d outside [0, %d)" % (i, int(sd.max() if sd.max() >= n else sd.min()), n))
-            flat.append(sd)
+            flat.append(sd.astype(np.int32))
             ptr[i + 1] = ptr[i] + len(sd)
         self.n_inst = len(seeds)
-        host = torch.empty(len(ptr) + int(ptr[-1]), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
-        packed = np.concatenate([ptr] + [f.astype(np.int32) for f in flat]) if flat else ptr
-        bg = np.concatenate([np.asarray(beta, dtype=np.float32), np.asarray(gamma, dtype=np.float32)])
-        if host is not None:
-            host.numpy()[:] = packed
-            hbg = torch.from_numpy(bg).pin_memory()
+        hi = torch.from_numpy(np.concatenate([ptr] + flat))
+        hf = torch.from_numpy(np.concatenate([np.asarray(beta, dtype=np.float32).reshape(-1),
+                                              np.asarray(gamma, dtype=np.float32).reshape(-1)]))
+        if torch.cuda.is_available():
+            hi, hf = hi.pin_memory(), hf.pin_memory()
+        self._host = (hi, hf)
+        if device is None:
+            self._bind(hi, hf)
         else:
-            host, hbg = torch.from_numpy(packed.astype(np.int32)), torch.from_numpy(bg)
-        self._host, self._hbg = host, hbg
-        dev_i = host.to(device, non_blocking=True)
-        dev_f = hbg.to(device, non_blocking=True)
-        self.seed_ptr, self.seeds = dev_i[:len(ptr)], dev_i[len(ptr):]
-        self.beta, self.gamma = dev_f[:self.n_inst], dev_f[self.n_inst:]
-        self.h2d_bytes = host.numel() * 4 + hbg.numel() * 4
-        self._keep = (dev_i, dev_f)
+            self._bind(hi.to(device, non_blocking=True), hf.to(device, non_blocking=True))
+
+    def _bind(self, ti, tf):
+        self._i, self._f = ti, tf
+        self.seed_ptr, self.seeds = ti[:self.n_inst + 1], ti[self.n_inst + 1:]
+        self.beta, self.gamma = tf[:self.n_inst], tf[self.n_inst:]
+        self.h2d_bytes = ti.numel() * 4 + tf.numel() * 4
+
+    def to(self, device):
+        """A copy of this set on `device` (two small asynchronous copies from pinned memory)."""
+        out = object.__new__(TrialSet)
+        out.n_inst, out._host = self.n_inst, self._host
+        out._bind(self._i.to(device, non_blocking=True), self._f.to(device, non_blocking=True))
+        return out
+
+    def copy_from(self, other, non_blocking=True):
+        """Overwrite this (device) set with another set of the same shape (e.g. the next batch of a pinned dataset)."""
+        if other._i.shape != self._i.shape or other._f.shape != self._f.shape:
+            raise ValueError("trial sets differ in shape")
+        self._i.copy_(other._i, non_blocking=non_blocking)
+        self._f.copy_(other._f, non_blocking=non_blocking)
+        return self
 
 
 def expand_trials(batch, trials, ldx=_lib.GNODE_TRIAL_LDX):

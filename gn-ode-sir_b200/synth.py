@@ -89,6 +89,14 @@ def ba_stress(seed=0):
     return barabasi_albert_csr_fast(2_000_000, 10, seed)
 
 
+def trial_parameters(n_nodes, trial_id, n_seeds=2):
+    """(seeds, beta, gamma) of synthetic trial `trial_id`: the compact descriptor of synthetic_trial's dense block."""
+    rng = np.random.RandomState(1000 + trial_id)
+    seeds = rng.choice(n_nodes, n_seeds, replace=False)
+    beta, gamma = rng.uniform(0.1, 0.5), rng.uniform(0.1, 0.5)
+    return seeds, beta, gamma
+
+
 def synthetic_trial(n_nodes, H, trial_id, n_seeds=2):
     """One [N, 3+H] input block in the layout main() of the reference builds (ode_nn_ngraph_sim.py:371-390): columns
     S0 | I0 | R0 | beta gamma 0...; seeds and rates drawn like monitorer-sim.py:116-119 from RandomState(1000 + id)."""

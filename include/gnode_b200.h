@@ -212,6 +212,21 @@ size_t gnode_l1_scratch_bytes(void);
 int gnode_l1_loss_grad(const float* probs, const double* labels, int64_t M, int32_t n_out, int32_t skip, float scale,
                        double* loss_out, float* grad_probs, void* scratch, void* stream);
 
+/* ---- N3: Monte-Carlo SIR labels ------------------------------------------------
+ * Replaces sir_torch (ode_nn.py:30-88; called from load_SIR_labels, ode_nn_ngraph_sim.py:198): `sims` independent
+ * discrete-time SIR simulations of T-1 steps from the seed set on graph g. Per step, with the nodes infected at its
+ * start: every (infected u, susceptible v) edge transmits with probability beta, every infected u recovers with
+ * probability gamma. One CTA per simulation, bit-packed state in shared memory, Philox4x32-10 keyed by
+ * (rng_seed; simulation, step, edge / node): the counts are a pure function of the arguments.
+ *   seeds   DEVICE int32[n_seeds] node ids (0-based positions in the CSR)
+ *   counts  DEVICE double[3][T][n]: number of simulations in which node v is S / I / R at step t, t >= 1; the t = 0
+ *           rows hold the 0/1 initial state (the reference assigns them instead of accumulating, ode_nn.py:54-55).
+ *           Labels = counts / sims, as load_SIR_labels divides.
+ *   workspace: gnode_mc_sir_workspace_bytes(g, T) bytes. Graphs of more than ~540k nodes are not supported. */
+size_t gnode_mc_sir_workspace_bytes(gnode_graph_t g, int32_t T);
+int gnode_mc_sir(gnode_graph_t g, const int32_t* seeds, int32_t n_seeds, float beta, float gamma, int32_t sims,
+                 int32_t T, uint64_t rng_seed, double* counts, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ def parse_args(argv=None):
     p.add_argument("--model", default="ode_nn", type=str)
     p.add_argument("--out_of_dist", default=False, action="store_true")
     args = p.parse_args(argv)
+    from gn_ode_sir_b200.rollout import check_hidden
+    check_hidden(args.hidden)                            # before any label is loaded or generated (Monte-Carlo runs are long)
     # seed sets arrive as strings "[a, b]" (monitorer-sim.py:64-65)
     args.I_indices = [[int(v) for v in str(s).strip("[]").split(",") if v.strip()] for s in args.I_indices]
     return args
@@ -95,19 +97,27 @@ def main(argv=None):
     xs, ys = build_inputs(args, n_nodes, labels)
     tr, va, te, idx_test = split_indices(args, len(xs))
 
+    # one process per GPU under torchrun: the trials of every global mini-batch are split across the ranks, one NCCL
+    # all-reduce of the parameter gradient per optimiser step (harness.run_epoch)
+    rank, world, device = harness.init_distributed()
+    shuffle_seed = harness.shared_seed()                                  # the same shuffle on every rank
+
     def loader(idx, batch_size, shuffle):
         ds = TensorDataset(torch.stack([xs[i] for i in idx]), torch.stack([ys[i] for i in idx]))
-        return DataLoader(ds, batch_size=batch_size, shuffle=shuffle)
+        return DataLoader(ds, batch_size=batch_size, shuffle=shuffle,
+                          generator=torch.Generator().manual_seed(shuffle_seed) if shuffle else None)
 
-    device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
     torch.set_default_dtype(torch.float32)
-    print(device)
+    if rank == 0:
+        print(device)
     if device.type != "cuda":
         raise SystemExit("ode_nn_ngraph_sim.py: the B200 GN-ODE rollout needs a CUDA device (there is no CPU path)")
     odefunc = ODEfunc(A, args.beta[0], args.gamma[0], args.hidden, device)
     model = ODEBlock(args.maxTime, args.deltaT, n_nodes, args.I_indices[0], args.hidden, odefunc, device).to(device)
     best = harness.fit(model, device, args.lr, args.epochs, loader(tr, args.batch_size, True),
                        loader(va, args.batch_size, False), loader(te, 1, False), args.maxTime, args.deltaT)
+    if rank != 0:
+        return
     if not args.out_of_dist:
         save_trial_to_csv(args, best["epoch"], best["val"], best["test"], 0, best["test_time"], 0)
     else:

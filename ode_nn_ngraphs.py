@@ -18,6 +18,7 @@ INSTANCES_PER_GRAPH = [36, 36, 36, 36, 36, 120]     # five training graphs, one 
 
 
 def parse_args(argv=None):
+    from gn_ode_sir_b200.rollout import check_hidden
     p = argparse.ArgumentParser(description="Neural ODE")
     p.add_argument("--lr", type=float, default=1e-2)
     p.add_argument("--epochs", type=int, default=100)
@@ -31,7 +32,9 @@ def parse_args(argv=None):
     p.add_argument("--dataset", default="none")
     p.add_argument("--train_val_test_ratio", nargs=3, type=float, default=[5e-1, 1e-1, 4e-1])
     p.add_argument("--model", default="ode_nn", type=str)
-    return p.parse_args(argv)
+    args = p.parse_args(argv)
+    check_hidden(args.hidden, need_marker=True)          # before any label is loaded or generated
+    return args
 
 
 def create_graphs(graph_label="none"):
@@ -55,14 +58,13 @@ def load_SIR_labels(graph, directory, I_indices, sim):
     return [v / sim for v in out] if graph == "wiki-vote" else out       # wiki-vote labels are raw counts
 
 
-def batches(items, batch_size, shuffle):
-    """Instances are concatenated along the node axis (ragged batch); shuffled once."""
-    order = np.random.permutation(len(items)) if shuffle else np.arange(len(items))
-    out = []
-    for i in range(0, len(items), batch_size):
-        grp = [items[j] for j in order[i:i + batch_size]]
-        out.append((torch.cat([g[0] for g in grp]), torch.cat([g[1] for g in grp])))
-    return out
+def batches(items, batch_size, shuffle, rng=None):
+    """Global mini-batches of instances (x_i, y_i, graph_id_i), shuffled once like the reference's loader
+    (ode_nn_ngraphs.py:179-196, :360). The harness concatenates each batch -- or, under torchrun, this rank's share of
+    it -- along the node axis (ragged batch) and names the instances' graphs, so the marker column is never read back
+    from the device."""
+    order = (rng or np.random).permutation(len(items)) if shuffle else np.arange(len(items))
+    return [[items[j] for j in order[i:i + batch_size]] for i in range(0, len(items), batch_size)]
 
 
 def main(argv=None):
@@ -84,17 +86,23 @@ def main(argv=None):
             x[:, 0] = 1.0 - x[:, 1]
             x[:, 3], x[:, 4], x[0, 5] = betas[i], gammas[i], gi + 1          # marker: first row names the graph
             y = torch.tensor(np.stack(load_SIR_labels(graph, d, s, args.sim), axis=-1)).transpose(0, 1)
-            (train if gi < len(INSTANCES_PER_GRAPH) - 1 else (val if len(val) < val_len else test)).append((x, y))
-    device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+            (train if gi < len(INSTANCES_PER_GRAPH) - 1 else (val if len(val) < val_len else test)).append((x, y, gi))
+    # one process per GPU under torchrun: every global mini-batch is split across the ranks by node count, the
+    # parameter gradient is summed with one NCCL all-reduce per optimiser step (harness.run_epoch)
+    rank, world, device = harness.init_distributed()
     torch.set_default_dtype(torch.float32)
-    print(device)
+    if rank == 0:
+        print(device)
     if device.type != "cuda":
         raise SystemExit("ode_nn_ngraphs.py: the B200 GN-ODE rollout needs a CUDA device (there is no CPU path)")
     odefunc = ODEfunc(A_list, args.hidden, device)
     model = ODEBlock(args.maxTime, args.deltaT, args.hidden, odefunc, device).to(device)
-    best = harness.fit(model, device, args.lr, args.epochs, batches(train, args.batch_size, True),
+    rng = np.random.RandomState(harness.shared_seed())                    # the same shuffle on every rank
+    best = harness.fit(model, device, args.lr, args.epochs, batches(train, args.batch_size, True, rng),
                        batches(val, args.batch_size, False), batches(test, args.batch_size, False),
                        args.maxTime, args.deltaT)
+    if rank != 0:
+        return
     csv_trials(args.path_to_save + "/Metrics-trials-" + os.path.relpath(args.dataset, "./real_graphs/"),
                ["trial", "model", "lr", "epochs", "deltaT", "maxTime", "hidden", "best_epoch", "val_loss",
                 "test_loss", "n_ode_time"],

@@ -267,3 +267,37 @@ def synthetic_trial(n_nodes, H, trial_id, graph_marker=0.0, n_seeds=2, dtype=tor
     if graph_marker:
         x[0, 5] = graph_marker
     return x
+
+
+# --------------------------------------------------------------------------
+# Monte-Carlo SIR labels: the process of /root/reference/ode_nn.py:30-88 (sir_torch), all simulations advanced
+# together with numpy (checker of the CUDA label generator; statistical comparison only -- the random streams differ)
+# --------------------------------------------------------------------------
+def mc_sir_counts(A, seed_set, beta, gamma, sims, T, rng):
+    """Returns counts [3, T, n] (S, I, R) over `sims` simulations; t = 0 rows hold the 0/1 initial state, as the
+    reference assigns them (ode_nn.py:54-55). Per step (ode_nn.py:57-76): every edge from a node infected at the start
+    of the step to a susceptible node transmits with probability beta; every such infected node recovers with
+    probability gamma."""
+    import numpy as np
+    A = A.tocoo()
+    src, dst = A.row, A.col
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    n = A.shape[0]
+    I = np.zeros((sims, n), dtype=bool)
+    I[:, list(seed_set)] = True
+    S = ~I
+    R = np.zeros_like(I)
+    counts = np.zeros((3, T, n))
+    counts[0, 0], counts[1, 0] = S[0], I[0]
+    for t in range(1, T):
+        hit = I[:, src] & S[:, dst] & (rng.random_sample((sims, len(src))) < beta)
+        newly = np.zeros((sims, n), dtype=bool)
+        rows, cols = np.nonzero(hit)
+        newly[rows, dst[cols]] = True
+        rec = I & (rng.random_sample((sims, n)) < gamma)
+        R |= rec
+        I = (I | newly) & ~rec
+        S &= ~newly
+        counts[0, t], counts[1, t], counts[2, t] = S.sum(0), I.sum(0), R.sum(0)
+    return counts

@@ -45,3 +45,22 @@ def test_ngraphs_variant_bit_exact():
     params = {k: v.detach().clone() for k, v in blk.state_dict().items()}
     got = orc.forward(x, params, orc.batch_coo(adjs, inst), orc.time_grid(10, 0.5))
     assert torch.equal(got, ref)
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason="needs /root/reference (build container only)")
+@pytest.mark.parametrize("name", ["karate", "dolphins", "fb-food", "fb-social", "openflights", "wiki-vote", "enron"])
+def test_cached_graph_pipeline_equals_reference_create_graph(name, tmp_path, monkeypatch):
+    """N2: pickle -> largest component -> CSR without networkx's adjacency_matrix, and its on-disk cache, give exactly the
+    matrix the reference's create_graph builds (ode_nn.py:394-414), for every shipped graph."""
+    import numpy as np
+    import gn_ode_sir_b200  # noqa: F401
+    from gn_ode_sir_b200 import harness
+    monkeypatch.setenv("GNODE_GRAPH_CACHE", str(tmp_path))
+    want = rh.load_reference_graph(name).tocsr()
+    want.sort_indices()
+    label = rh.REFERENCE_ROOT + "/real_graphs/" + name
+    for attempt in ("built", "cached"):
+        G, A = harness.load_graph(label)
+        assert A.shape == want.shape and np.array_equal(A.indptr, want.indptr) and np.array_equal(A.indices, want.indices), attempt
+        assert G.number_of_nodes() == want.shape[0]
+    assert len(list(tmp_path.iterdir())) == 1                       # the second load came from the cache file

@@ -1,6 +1,7 @@
 """Rollout throughput over the BASELINE.json / SURVEY 8d configurations (inference, inputs resident in HBM, CUDA events):
-graph sizes of the reference's datasets as BA stand-ins (the pickles do not travel to the GPU box), trial counts and
-maxTime sweep on the epinions stand-in, and a heavier-tailed variant (hub degree ~3k like soc-Epinions1)."""
+the SHIPPED real graphs (their CSR travels in tests/golden/*.npz and tests/golden/graphs/enron.npz; the pickles do not
+exist on the GPU box) next to Barabasi-Albert stand-ins of the same size, trial counts and maxTime sweep on the epinions
+stand-in, and a heavier-tailed variant (hub degree ~3k like soc-Epinions1)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, scipy.sparse, torch
@@ -55,7 +56,30 @@ def run(name, A, B, maxTime, reps=3):
     torch.cuda.empty_cache()
 
 
+def real_graph(name):
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    fixture = {"karate": ("sim_karate_b1", 0), "dolphins": ("sim_dolphins_b4", 0), "fb-food": ("sim_fbfood_b2", 0),
+               "fb-social": ("sim_fbsocial_b1", 0), "openflights": ("sim_openflights_b2", 0), "wiki-vote": ("sim_wikivote_b2", 0)}
+    if name == "enron":
+        z = np.load(os.path.join(root, "graphs", "enron.npz")); ip, ix = z["indptr"], z["indices"]
+    else:
+        z = np.load(os.path.join(root, fixture[name][0] + ".npz")); ip, ix = z["g0_indptr"], z["g0_indices"]
+    n = len(ip) - 1
+    return scipy.sparse.csr_matrix((np.ones(len(ix), dtype=np.int64), ix, ip), shape=(n, n))
+
+
 ep = synth.epinions_standin(0)
+print("--- shipped real graphs (reference real_graphs/*.pkl, largest connected component)")
+run("karate (real)", real_graph("karate"), 1, 20)
+run("karate (real)", real_graph("karate"), 8, 20)
+for B in (8, 64, 512):
+    run("fb-social (real)", real_graph("fb-social"), B, 20)
+run("openflights (real)", real_graph("openflights"), 512, 20)
+for B in (64, 512):
+    run("wiki-vote (real)", real_graph("wiki-vote"), B, 20)
+for B in (32, 128, 256):
+    run("enron (real)", real_graph("enron"), B, 20)
+print("--- Barabasi-Albert stand-ins of the same sizes")
 run("karate-size BA(34,2)", synth.barabasi_albert_csr(34, 2, 0), 1, 20)
 for B in (8, 64, 512):
     run("fb-social-size BA(1893,7)", synth.barabasi_albert_csr(1893, 7, 0), B, 20)
