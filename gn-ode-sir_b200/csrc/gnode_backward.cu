@@ -200,16 +200,23 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a
             }
             AI = gather_row(a.Ip, ci, e0, deg, row0, l, lane);
         }
+        // Grid points without a cotangent (sparse dL/dprobs: only the rows int(i/deltaT) enter the loss) have D = 0:
+        // no decoder backward, the state planes are not read and the adjoint is not rewritten
+        const bool dec = a.gP != nullptr;                     // kernel argument: uniform
         float4 c[3], d[3];
+        if (dec) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) c[k] = valid ? ldg4_stream(a.y + k * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        decoder_backward_row(c, (valid && a.gP) ? a.gP + (size_t)g * 3 : nullptr, W3s, small, l, valid, d, acc);
+            for (int k = 0; k < 3; ++k) c[k] = valid ? ldg4_stream(a.y + k * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            decoder_backward_row(c, valid ? a.gP + (size_t)g * 3 : nullptr, W3s, small, l, valid, d, acc);
+        }
         if (valid) {
             float4 av[3];
+            av[0] = ldg4(a.a + off); av[1] = ldg4(a.a + plane + off);
+            if (dec) {
+                av[2] = ldg4(a.a + 2 * plane + off);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) av[k] = ldg4(a.a + k * plane + off);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { av[k].x += d[k].x; av[k].y += d[k].y; av[k].z += d[k].z; av[k].w += d[k].w; }
+                for (int k = 0; k < 3; ++k) { av[k].x += d[k].x; av[k].y += d[k].y; av[k].z += d[k].z; av[k].w += d[k].w; }
+            }
             if (!a.only_dec) {
                 const float4 sp = ldg4(a.Sp + off);
                 float4 G;
@@ -218,10 +225,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a
                 stg4(a.G + off, G);
                 stg4(a.AI + off, AI);
             }
+            if (dec) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) stg4(a.a + k * plane + off, av[k]);
+                for (int k = 0; k < 3; ++k) stg4(a.a + k * plane + off, av[k]);
+            }
         }
     }
+    if (a.gP == nullptr) return;                               // no decoder gradients were accumulated
     // block reduction in a fixed order (deterministic), then this block's slot += result
 #pragma unroll
     for (int i = 0; i < 16; ++i) red[hw][l][i] = acc.w3[i];
@@ -740,6 +750,50 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
     }
     const size_t M = (size_t)b->M;
     unsigned char* ws = (unsigned char*)workspace;
+    // Launch-bound batches (the reference's own monitorer runs use batch sizes 1 and 8: 4 launches per reverse step of
+    // a few microseconds each): the whole sweep is captured once into a CUDA graph, keyed by every pointer and scalar
+    // that enters it, and replayed while the caller keeps handing over the same buffers (a training loop under torch's
+    // caching allocator does). GNODE_BWD_GRAPH=0 disables it.
+    static const bool graphs_on = !(getenv("GNODE_BWD_GRAPH") && atoi(getenv("GNODE_BWD_GRAPH")) == 0);
+    uint64_t key = 0;
+    bool use_graph = false, capturing = false;
+    cudaStream_t user_stream = stream;
+    if (graphs_on && b->n_tiles <= 4 * b->sm_count) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+            auto mix = [&](const void* ptr, size_t n) {
+                const unsigned char* c = (const unsigned char*)ptr;
+                if (key == 0) key = 1469598103934665603ull;
+                for (size_t i = 0; i < n; ++i) { key ^= c[i]; key *= 1099511628211ull; }
+            };
+            const void* ptrs[] = {x, traj, grad_probs, grads_out, workspace, stream_};
+            mix(ptrs, sizeof(ptrs)); mix(p, sizeof(*p)); mix(&ldx, sizeof(ldx)); mix(&T, sizeof(T));
+            mix(&grad_mode, sizeof(grad_mode)); mix(dt_host, sizeof(float) * (size_t)(T > 1 ? T - 1 : 0));
+            mix(sel.slot.data(), sizeof(int) * sel.slot.size());
+            const int vk = vjp_kernel_choice();
+            mix(&vk, sizeof(vk));
+            use_graph = true;
+            for (auto& e : b->bwd_graphs)
+                if (e.key == key) {
+                    GN_CUDA(cudaGraphLaunch((cudaGraphExec_t)e.exec, stream));
+                    gnode::g_launches += e.kernels;
+                    return GNODE_OK;
+                }
+            // captured on a stream of the handle's own (the caller's may be the legacy default stream, which cannot be
+            // captured); the instantiated graph is then launched into the caller's stream
+            if (!b->capture_stream) {
+                cudaStream_t cs_ = nullptr;
+                GN_CUDA(cudaStreamCreateWithFlags(&cs_, cudaStreamNonBlocking));
+                b->capture_stream = (void*)cs_;
+            }
+            user_stream = stream;
+            stream = (cudaStream_t)b->capture_stream;
+            GN_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            capturing = true;
+        }
+    }
+    const int64_t launches_before = gnode::g_launches;
+    auto enqueue = [&]() -> int {
     BwdArgs a;
     a.bv = gn_view(b);
     a.x = x; a.ldx = ldx; a.p = *p;
@@ -807,5 +861,28 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
     reduce_partials_kernel<<<(DEC_COUNT + 255) / 256, 256, 0, stream>>>(pdec, pl.grid_row, DEC_COUNT,
                                                                         grads_out + GNODE_GRAD_OFF_L3_W);
     GN_LAUNCH_CHECK();
+    return GNODE_OK;
+    };
+    rc = enqueue();
+    if (!capturing) return rc;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (rc != GNODE_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == GNODE_OK) { set_error("gnode_rollout_backward: graph capture failed: %s", cudaGetErrorString(ce)); rc = GNODE_ERR_CUDA; }
+        return rc;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { set_error("gnode_rollout_backward: cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return GNODE_ERR_CUDA; }
+    const int64_t kernels = gnode::g_launches - launches_before;          // counted while capturing; nothing ran yet
+    if (b->bwd_graphs.size() >= 8) {                                       // small LRU: drop the oldest
+        cudaGraphExecDestroy((cudaGraphExec_t)b->bwd_graphs.front().exec);
+        b->bwd_graphs.erase(b->bwd_graphs.begin());
+    }
+    b->bwd_graphs.push_back({key, (void*)exec, kernels});
+    GN_CUDA(cudaGraphLaunch(exec, user_stream));
+    (void)use_graph;
     return GNODE_OK;
 }

@@ -93,6 +93,10 @@ struct gnode_batch {
     int4* d_sub_meta = nullptr;      // [2 n_tiles] the same for the two 64-row halves of every tile
     int device = 0;
     int sm_count = 0;
+    // captured reverse sweeps of launch-bound batches (gnode_rollout_backward): key of all arguments -> cudaGraphExec_t
+    struct BwdGraph { uint64_t key; void* exec; int64_t kernels; };
+    std::vector<BwdGraph> bwd_graphs;
+    void* capture_stream = nullptr;      // cudaStream_t used only to capture those graphs
 };
 
 // Kernel-side view of a batch.

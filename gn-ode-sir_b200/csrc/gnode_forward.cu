@@ -49,6 +49,7 @@ struct StepArgs {
     int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
     int* counter;         // dynamic tile scheduler (one zeroed int per launch) or null = static striding
     gnode_params_t p;
+    int relay_off;        // 1: hub rows are walked serially by one half-warp (gnode_set_hub_relay(0): the relay's bitwise check)
     int use_tma;          // dual kernel: I'_{k+1} tiles leave shared memory through TMA stores described by tm_ip_out
     // persistent rollout (dual kernel, cooperative launch): the kernel runs the Euler steps k0 .. k1-1 itself, with a
     // grid barrier between steps; per-step pointers are derived from the bases below (n_steps == 0: one step from the
@@ -309,396 +310,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Fused Euler step, tensor-core path (the production kernel for MODE_STEP).
-//
-// Per 128-row tile (2 CTAs of 512 threads per SM; all block barriers are __syncthreads):
-//   P1  S_k tile (prefetched into registers during the previous tile's second GEMM) -> tf32 hi/lo
-//       operand tiles; the tile's rowptr slice -> shared memory                              | S1
-//   P2  one thread issues GEMM1 (tcgen05, 32 MMAs); meanwhile all threads stage the tile's colidx
-//       slice (as global row ids) in shared memory; then all 16 warps run the S' epilogue     | S2
-//   P3  row-per-half-warp: neighbour sum with indices from shared memory (no dependent index
-//       round trips), SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles            | S3
-//   P4  one thread issues GEMM2; all threads prefetch the next tile's S rows into registers; all
-//       warps run the I' epilogue into the staging tile                                       | S4
-//   P5  coalesced store of I'_{k+1}                                                           | S5
-constexpr int CSR_CAP = 2816;                   // colidx entries staged per tile (rest read from HBM/L2)
-constexpr int T_X = 0;                          // 32 KB  A operand hi  (parks the neighbour sums between the two row phases)
-constexpr int T_L = 32768;                      // 32 KB  A operand lo / S' / I' staging
-constexpr int T_WHI = 65536;                    // 16 KB
-constexpr int T_WLO = T_WHI + H * H * 4;        // 16 KB
-constexpr int T_B = T_WLO + H * H * 4;          // bias [64]
-constexpr int T_W3 = T_B + H * 4;               // linear3.weight [4][64]
-constexpr int T_SMALL = T_W3 + 4 * H * 4;       // b3[4], w2[4], b2
-constexpr int T_MBAR = T_SMALL + 64;            // mbarrier (8) + tmem slot (4) + next-tile slot (4)
-constexpr int T_BG = T_MBAR + 32;               // beta[TILE], gamma[TILE] of the tile
-constexpr int T_RP = T_BG + 2 * TILE * 4;       // rowptr slice [TILE + 1] (+pad)
-constexpr int T_CI = T_RP + 544;                // colidx slice [CSR_CAP] as global row ids
-constexpr int T_TOTAL = T_CI + CSR_CAP * 4 + 1024;
-static_assert(2 * (T_TOTAL + 1024) <= 232448, "two CTAs per SM must fit in shared memory");
-
+// small device helpers of the pipelined step kernels
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-
 // TMA tensor store of one box (shared memory -> global), bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, uint64_t pol) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
                  ::"l"(tm), "r"(c0), "r"(c1), "r"(umma::smem_u32(smem_src)), "l"(pol) : "memory");
 }
 
-// decoder + softmax with a 20-shuffle butterfly: after 4 halving exchange stages lane l of the
-// half-warp holds the complete pre-activation hid[c = l>>2][m = l&3] (c = 3 is padding).
-__device__ __forceinline__ void decode_row_bfly(float4 s, float4 i, float4 r, const float* W3s, const float* small,
-                                                int l, int lane, bool valid, float* probs_row) {
-    float v[16];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const float4 w = *reinterpret_cast<const float4*>(W3s + m * H + 4 * l);
-        v[m] = dot4(s, w); v[4 + m] = dot4(i, w); v[8 + m] = dot4(r, w); v[12 + m] = 0.f;
-    }
-    const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0, b1 = (l & 2) != 0, b0 = (l & 1) != 0;
-    float a8[8], a4[4], a2[2];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a8[k] = (b3 ? v[8 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b3 ? v[k] : v[8 + k], 8);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a4[k] = (b2 ? a8[4 + k] : a8[k]) + __shfl_xor_sync(0xffffffffu, b2 ? a8[k] : a8[4 + k], 4);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) a2[k] = (b1 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b1 ? a4[k] : a4[2 + k], 2);
-    const float hid = (b0 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? a2[0] : a2[1], 1);
-    const int m = l & 3;
-    float t = small[4 + m] * fmaxf(hid + small[m], 0.f);          // w2[m] * relu(hid + b3[m])
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    const float o = t + small[8];
-    const int hb = lane & 16;
-    const float oS = __shfl_sync(0xffffffffu, o, hb + 0), oI = __shfl_sync(0xffffffffu, o, hb + 4),
-                oR = __shfl_sync(0xffffffffu, o, hb + 8);
-    // softmax; exp(x) = 2^(x log2 e) with x <= 0 (absolute error of each probability < 4e-7)
-    const float mx = fmaxf(oS, fmaxf(oI, oR));
-    const float eS = ex2_approx((oS - mx) * 1.4426950408889634f), eI = ex2_approx((oI - mx) * 1.4426950408889634f),
-                eR = ex2_approx((oR - mx) * 1.4426950408889634f);
-    const float inv = rcp_approx(eS + eI + eR);
-    if (valid && l < 3) probs_row[l] = (l == 0 ? eS : (l == 1 ? eI : eR)) * inv;
-}
-
-// Neighbour sum of one row with the tile's indices staged in shared memory: full batches of 8
-// unpredicated loads, one predicated tail batch. Sequential ascending-column accumulation.
-__device__ __forceinline__ float4 gather_smem(const float* __restrict__ lane_base, const int* cp, int deg, uint64_t pol) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int j = 0;
-    for (; j + 8 <= deg; j += 8) {
-        float4 v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
-    }
-    // tail (< 8 neighbours): one unpredicated batch of 4 and up to 3 predicated loads, all issued
-    // before the first add so that they share one memory round trip
-    const int rem = deg - j;
-    const bool four = rem >= 4;
-    const int j3 = j + (four ? 4 : 0), r3 = rem & 3;
-    float4 v4[4], v3[3];
-    if (four) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v4[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        v3[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < r3) v3[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j3 + k] * H, pol);
-    }
-    if (four) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { acc.x += v4[k].x; acc.y += v4[k].y; acc.z += v4[k].z; acc.w += v4[k].w; }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-        if (k < r3) { acc.x += v3[k].x; acc.y += v3[k].y; acc.z += v3[k].z; acc.w += v3[k].w; }
-    return acc;
-}
-
-// Warp-uniform variant: both half-warps of the warp (two adjacent rows) run the same trip counts
-// (bounded by the larger degree, loads predicated per row), so the warp never diverges; rows with up to
-// 11 neighbours complete in ONE memory round trip (8 + 3 loads in flight per lane).
-__device__ __forceinline__ float4 gather_smem_uniform(const float* __restrict__ lane_base, const int* cp, int deg, uint64_t pol) {
-    const int degm = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int j = 0;
-    for (; degm - j > 11; j += 8) {
-        float4 v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j + k < deg) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
-    }
-    {
-        float4 v[11];
-#pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j + k < deg) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j + k] * H, pol);
-        }
-#pragma unroll
-        for (int k = 0; k < 11; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
-    }
-    return acc;
-}
-
-template <bool FAST>
-__global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* Xs = smem + T_X;
-    unsigned char* Ls = smem + T_L;
-    float* bs = reinterpret_cast<float*>(smem + T_B);
-    float* W3s = reinterpret_cast<float*>(smem + T_W3);
-    float* small = reinterpret_cast<float*>(smem + T_SMALL);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T_MBAR);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + T_MBAR + 8);
-    int* seq_slot = reinterpret_cast<int*>(smem + T_MBAR + 12);
-    int* row_ctr = reinterpret_cast<int*>(smem + T_MBAR + 16);
-    float* bg_s = reinterpret_cast<float*>(smem + T_BG);
-    int* rp_s = reinterpret_cast<int*>(smem + T_RP);
-    int* ci_s = reinterpret_cast<int*>(smem + T_CI);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = tid & 15, hw = tid >> 4;
-    const int M = a.bv.M;
-    const size_t plane = (size_t)M * H;
-    const int n_tiles = a.bv.n_tiles;
-    // every tile access of this thread is chunk l of rows hw + 32*i: one swizzled offset + i * 4 KB
-    const int off0 = sw_off(hw, l);
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-
-    umma::prepare_weights(a.p.lin_w, smem + T_WHI, smem + T_WLO, tid, NTHREADS);
-    if (warp == 0) umma::tmem_alloc(tslot, umma::TMEM_COLS);
-    if (tid == 0) {
-        umma::mbar_init(mbar, 1);
-        *seq_slot = a.counter ? atomicAdd(a.counter, 1) : (int)blockIdx.x;
-    }
-    umma::fence_before_sync();
-    if (tid < H) bs[tid] = a.p.lin_b[tid];
-    if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
-    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
-    if (tid == 0) small[8] = a.p.s2_b[0];
-    __syncthreads();
-    umma::fence_after_sync();
-    umma::Ctx cx;
-    cx.tmem = *tslot; cx.bar = mbar; cx.phase = 0;
-    cx.whi = umma::smem_u32(smem + T_WHI); cx.wlo = umma::smem_u32(smem + T_WLO);
-    const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
-
-    int seq = *seq_slot;
-    // HBM -> L2 one tile ahead: the S tile (operand of GEMM1), the own-row operands of the row phases, and the
-    // I' rows of the same tile one instance (trial) ahead, kept in L2 for that instance's gathers
-    auto prefetch_rows = [&](int2 sc) {            // thread 0; sc = schedule entry {tile, look-ahead row}
-        if (a.dbg & 32) return;
-        const int t0 = sc.x * TILE;
-        const uint32_t bytes = (uint32_t)min(TILE, M - t0) * H * 4;
-        prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
-        prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
-        prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
-        prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
-        if (sc.y >= 0) prefetch_l2_bulk_hint(a.ip_in + (size_t)sc.y * H, (uint32_t)min(TILE, M - sc.y) * H * 4, pol_keep);
-    };
-    if (tid == 0 && seq < n_tiles) prefetch_rows(a.bv.sched[seq]);
-
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-#define GN_TICK(i) if (a.tbuf && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
-    while (seq < n_tiles) {
-        // next tile of this CTA: the atomic is issued now, its result is first used after the gather phase
-        int nseq = 0;
-        if (tid == 0) nseq = a.counter ? atomicAdd(a.counter, 1) : seq + (int)gridDim.x;
-        const int tile = a.bv.tile_order[seq];
-        const int tile0 = tile * TILE;
-        const int nrows = min(TILE, M - tile0);
-        const int inst0 = a.bv.tile_inst[tile];
-        const int i_row0 = a.bv.inst[inst0].row0;
-        const bool single = (tile0 + nrows <= i_row0 + a.bv.inst[inst0].n);   // whole tile inside one instance
-        const int32_t* i_colidx = a.bv.inst[inst0].colidx;
-
-        // ---- P1: operand tiles for GEMM1 (S_k rows from L2); rowptr slice, beta/gamma of the tile
-        {
-            const float* src = a.y_in + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
-            float4 sreg[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                sreg[i] = (hw + 32 * i < nrows) ? ldg4(src + (size_t)i * 32 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 hi, lo;
-                umma::tf32_split4(sreg[i], hi, lo);
-                sts4(Xs, off0 + i * 4096, hi);
-                sts4(Ls, off0 + i * 4096, lo);
-            }
-        }
-        umma::fence_proxy_async();
-        if (tid == 0) *row_ctr = 0;
-        if (single && tid <= nrows) rp_s[tid] = __ldg(a.bv.inst[inst0].rowptr + (tile0 - i_row0 + tid));
-        if (tid >= 256 && tid < 256 + nrows) bg_s[tid - 256] = a.beta[tile0 + tid - 256];
-        if (tid >= 384 && tid < 384 + nrows) bg_s[TILE + tid - 384] = a.gamma[tile0 + tid - 384];
-        __syncthreads();                                                        // S1
-        GN_TICK(0)
-        // ---- P2: GEMM1 || colidx staging ; S' epilogue
-        if (!(a.dbg & 16) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
-        int ebase = 0;
-        if (single) {
-            ebase = rp_s[0];
-            const int ecnt = min(rp_s[nrows] - ebase, CSR_CAP);
-            for (int j = tid; j < ecnt; j += NTHREADS) ci_s[j] = i_colidx[ebase + j] + i_row0;
-        }
-        if (!(a.dbg & 16)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
-        __syncthreads();                                                        // S2
-        GN_TICK(1)
-        // ---- P3a: neighbour sums AI -> parked in the (now dead) hi operand tile. Row pairs are handed out
-        //      dynamically (shared-memory counter) so that hub rows do not leave the other warps idle.
-        {
-            const float* lane_base = a.ip_in + 4 * l;
-            if (single) {
-                for (;;) {
-                    int p = 0;
-                    if (lane == 0) p = atomicAdd(row_ctr, 1);
-                    p = __shfl_sync(0xffffffffu, p, 0);
-                    if (p >= TILE / 2) break;
-                    const int rr = 2 * p + (lane >> 4);
-                    int e_rel = 0, deg = 0;
-                    if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr]; }
-                    const int over = (e_rel + deg > CSR_CAP) ? 1 : 0;
-                    float4 acc;
-                    if (__any_sync(0xffffffffu, over)) {         // hub tile: indices beyond the staged slice
-                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int j = 0; j < deg; ++j) {
-                            const int c = i_colidx[ebase + e_rel + j] + i_row0;
-                            const float4 v = ldg4_hint(lane_base + (size_t)c * H, pol_keep);
-                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                        }
-                        __syncwarp();
-                    } else {
-                        acc = gather_smem_uniform(lane_base, ci_s + e_rel, deg, pol_keep);
-                    }
-                    sts4(Xs, sw_off(rr, l), acc);
-                }
-            } else {                                         // tile spans several (small) instances
-                int inst = inst0;
-#pragma unroll 1
-                for (int it = 0; it < TILE / 32; ++it) {
-                    const int rr = hw + 32 * it;
-                    int row0 = 0, e0 = 0, deg = 0;
-                    const int32_t* ci = nullptr;
-                    if (rr < nrows) {
-                        const int g = tile0 + rr;
-                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
-                        const GnInstance I = a.bv.inst[inst];
-                        row0 = I.row0; ci = I.colidx;
-                        e0 = I.rowptr[g - row0];
-                        deg = I.rowptr[g - row0 + 1] - e0;
-                    }
-                    const float4 acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
-                    sts4(Xs, off0 + it * 4096, acc);
-                }
-            }
-        }
-        __syncthreads();                                                        // S2b: every AI row is parked
-        GN_TICK(2)
-        int2 nsched = make_int2(0, -1);
-        if (tid == 0) {
-            *seq_slot = nseq;
-            if (nseq < n_tiles) nsched = a.bv.sched[nseq];
-        }
-        // ---- P3b: SIR update, stores, decoder; I_{k+1} hi/lo -> operand tiles. The own-row loads of row
-        //      it+1 are issued before the decoder of row it, so their L2 latency hides behind its arithmetic.
-        {
-            float4 s, iv, rv, ipo;
-            auto load_own = [&](int it) {
-                const int rr = hw + 32 * it;
-                s = make_float4(1.f, 1.f, 1.f, 1.f); iv = s; rv = s; ipo = s;
-                if (rr < nrows && !(a.dbg & 4)) {
-                    const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                    s = ldg4_hint(a.y_in + off, pol_stream);
-                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
-                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
-                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
-                }
-            };
-            load_own(0);
-#pragma unroll 1
-            for (int it = 0; it < TILE / 32; ++it) {
-                const int rr = hw + 32 * it;
-                const bool valid = rr < nrows;
-                const size_t off = (size_t)(tile0 + (valid ? rr : 0)) * H + 4 * l;
-                float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
-                if (valid) {
-                    const float4 acc = lds4(Xs, off0 + it * 4096);
-                    const float4 sp = lds4(Ls, off0 + it * 4096);
-                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
-#define GN_COMP(c)                                                                  \
-    {                                                                               \
-        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
-        const float dR = __fmul_rn(ga, ipo.c);                                      \
-        const float dI = __fsub_rn(-dS, dR);                                        \
-        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
-        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
-        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
-    }
-                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
-#undef GN_COMP
-                    stg4_hint(a.y_out + off, sn, pol_stream);
-                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
-                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
-                    float4 hi, lo;
-                    umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
-                    sts4(Xs, off0 + it * 4096, hi);
-                    sts4(Ls, off0 + it * 4096, lo);
-                }
-                if (it + 1 < TILE / 32) load_own(it + 1);
-                if (a.probs != nullptr && !(a.dbg & 1))
-                    decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
-            }
-        }
-        GN_TICK(3)
-        umma::fence_proxy_async();
-        __syncthreads();                                                        // S3
-        GN_TICK(4)
-        // ---- P4: GEMM2 || prefetch of the next tile ; I' epilogue
-        if (!(a.dbg & 8) && tid == 0) umma::issue_split_gemm(cx, xs_addr, ls_addr);
-        const int seq_next = *seq_slot;
-        if (tid == 0 && seq_next < n_tiles) prefetch_rows(nsched);
-        if (!(a.dbg & 8)) umma::epilogue_sigmoid<FAST>(cx, Ls, bs, warp, lane);
-        __syncthreads();                                                        // S4
-        GN_TICK(5)
-        // ---- P5: coalesced store of I'_{k+1}
-        {
-            float* dst = a.ip_out + (size_t)tile0 * H + (size_t)hw * H + 4 * l;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (hw + 32 * i < nrows) stg4_hint(dst + (size_t)i * 32 * H, lds4(Ls, off0 + i * 4096), pol_stream);
-        }
-        __syncthreads();                                                        // S5
-        GN_TICK(6)
-        seq = seq_next;
-    }
-    if (a.tbuf && tid == 0)
-        for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
-#undef GN_TICK
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
-}
-
-
 // ---------------------------------------------------------------------------------------------
 // Fused Euler step, "dual" kernel (the production kernel for MODE_STEP).
 //
-// ONE CTA of 1024 threads per SM = two independent 512-thread halves, each running the phase pipeline of
-// step_tc_kernel on its own tiles (own operand tiles, CSR slice, mbarrier, TMEM accumulator, named barrier),
+// ONE CTA of 1024 threads per SM = two independent 512-thread halves, each running a phase pipeline (P1 .. P5
+// below) on its own tiles (own operand tiles, CSR slice, mbarrier, TMEM accumulator, named barrier),
 // while the W operand tiles, bias and decoder constants are shared. The shared-memory saved by not duplicating
 // W pays for the N = 80 operand [W; W3]: the decoder's hidden layer (linear3, ode_nn_ngraph_sim.py:172-176) of
 // the S and I blocks comes out of the two GEMMs that the step needs anyway, in accumulator columns 64..67:
@@ -706,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_tc_kernel(const StepArgs a) 
 //   GEMM2: I_{k+1} [W; W3]^T -> I'_{k+1}     and hid(I_{k+1})  -> HBM side buffer hid_i (16 B / row), read by step k+1
 //   hid(R_k): 16 FMAs + a 5-shuffle butterfly per lane in the update phase (R has no GEMM)
 // so the launch of step k emits probs[k] (the softmax of its INPUT state, one thread per row) instead of probs[k+1];
-// the host decodes the last state with decode_kernel. Differences from step_tc_kernel besides that:
+// the host decodes the last state with decode_kernel. Further:
 //   * the tcgen05.commit mbarrier is awaited with a suspend-time hint (the hardware parks the warps; no spin loop);
 //   * no tile starts with a chain of dependent loads: an idle warp resolves the next tile's metadata during the
 //     second GEMM, the next tile's S rows are prefetched into registers during the I' store, and the CSR slice,
@@ -977,7 +605,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         if (m.seq >= n_tiles) break;
         const int tile0 = m.tile0, nrows = m.nrows, i_row0 = m.i_row0, ebase = m.ebase;
         const bool single = (m.single & 1) != 0;
-        const bool relay = (m.single & 2) != 0 && !(a.dbg & 4194304);   // the tile has isolated hub rows (host cost model)
+        const bool relay = (m.single & 2) != 0 && !(a.dbg & 4194304) && !a.relay_off;   // the tile has isolated hub rows (host cost model)
 
         // ---- P1: operand tiles for GEMM1 (S_k rows); the tile's CSR slice, beta/gamma -> smem
         //      (every address is known from the metadata: all these loads are in flight together)
@@ -1364,350 +992,9 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ y
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-specialised fused Euler step (1 CTA of 640 threads per SM, two tile slots in flight).
-//
-//   PE-A group (4 warps = the four TMEM lane quarters): for tile t in slot t&1 (after slot_free)
-//       S_k rows -> tf32 hi/lo operand tiles; rowptr / colidx / beta / gamma slices -> smem;
-//       GEMM1 (tcgen05) ; epilogue S' -> smem                              => csr_ready, sp_ready
-//   PE-B group (4 warps): waits for the workers' I_{k+1} operand tiles, GEMM2, epilogue, coalesced
-//       I'_{k+1} store                                                      => slot_free
-//   worker group (16 warps): per tile, row-per-half-warp: own-row loads + neighbour gather (up to 12
-//       row loads in flight per lane), SIR update, state stores, decoder, I_{k+1} hi/lo -> operand
-//       tiles                                                              => a2_ready
-// The groups meet only through mbarriers, so the gather/update stream of tile t overlaps the
-// GEMM/epilogue work of tiles t-1 and t+1; there is no block-wide barrier in the steady state.
-constexpr int WS_WORKERS = 512, WS_PE = 128, WS_THREADS = WS_WORKERS + 2 * WS_PE;   // workers | PE-A | PE-B
-constexpr int WS_CAP = 2816;
-constexpr int W_WHI = 0, W_WLO = 16384, W_SLOT = 32768, W_SLOT_BYTES = 65536;
-constexpr int W_CI = W_SLOT + 2 * W_SLOT_BYTES, W_CI_BYTES = WS_CAP * 4;
-constexpr int W_RP = W_CI + 2 * W_CI_BYTES, W_RP_BYTES = 544;
-constexpr int W_BG = W_RP + 2 * W_RP_BYTES, W_BG_BYTES = 2 * TILE * 4;
-constexpr int W_B = W_BG + 2 * W_BG_BYTES;
-constexpr int W_W3 = W_B + H * 4;
-constexpr int W_SMALL = W_W3 + 4 * H * 4;
-constexpr int W_BARS = W_SMALL + 64;          // 12 mbarriers (96 B), tmem slot, slot meta
-constexpr int W_TOTAL = W_BARS + 160 + 1024;
-static_assert(W_TOTAL <= 232448, "shared memory budget");
-enum { BAR_CSR = 0, BAR_SP = 2, BAR_A2 = 4, BAR_M1 = 6, BAR_M2 = 8, BAR_FREE = 10 };   // + slot
-
-// all lanes poll in lockstep (same issue cost as one lane, and no intra-warp divergence is introduced)
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-    (void)lane;
-    umma::mbar_wait(bar, parity);
-}
-
-template <bool FAST>
-__global__ void __launch_bounds__(WS_THREADS, 1) step_ws_kernel(const StepArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* bs = reinterpret_cast<float*>(smem + W_B);
-    float* W3s = reinterpret_cast<float*>(smem + W_W3);
-    float* small = reinterpret_cast<float*>(smem + W_SMALL);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W_BARS);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + W_BARS + 96);
-    int* meta = reinterpret_cast<int*>(smem + W_BARS + 112);       // [slot][4]: tile, single
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    // warp index made provably warp-uniform, so that the role branches below are convergent for the compiler
-    // (otherwise every __shfl_sync inside them is compiled to the slow convergence-checking sequence)
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int M = a.bv.M;
-    const size_t plane = (size_t)M * H;
-    const int n_tiles = a.bv.n_tiles;
-
-    umma::prepare_weights(a.p.lin_w, smem + W_WHI, smem + W_WLO, tid, WS_THREADS);
-    if (warp == 0) umma::tmem_alloc(tslot, 256);
-    if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            umma::mbar_init(bars + BAR_CSR + s, 1);
-            umma::mbar_init(bars + BAR_SP + s, 1);
-            umma::mbar_init(bars + BAR_A2 + s, WS_WORKERS);
-            umma::mbar_init(bars + BAR_M1 + s, 1);
-            umma::mbar_init(bars + BAR_M2 + s, 1);
-            umma::mbar_init(bars + BAR_FREE + s, 1);
-        }
-    }
-    umma::fence_before_sync();
-    if (tid < H) bs[tid] = a.p.lin_b[tid];
-    if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
-    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
-    if (tid == 0) small[8] = a.p.s2_b[0];
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem = *tslot;
-    const uint32_t whi = umma::smem_u32(smem + W_WHI), wlo = umma::smem_u32(smem + W_WLO);
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-    long long tacc[3] = {0, 0, 0};
-    long long tprev = clock64();
-#define WS_TICK(i) if (a.tbuf) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
-
-    if (warp < WS_WORKERS / 32) {
-        // =============================== workers ===============================
-        const int l = tid & 15, hw = tid >> 4;
-        const int off0 = sw_off(hw, l);
-        const float* lane_base = a.ip_in + 4 * l;
-        for (int t = 0;; ++t) {
-            const int s = t & 1;
-            const uint32_t par = (uint32_t)(t >> 1) & 1u;
-            mbar_wait_warp(bars + BAR_CSR + s, par, lane);
-            WS_TICK(0)
-            const int tile = __shfl_sync(0xffffffffu, meta[4 * s], 0);
-            if (tile < 0) break;
-            const bool single = __shfl_sync(0xffffffffu, meta[4 * s + 1], 0) != 0;
-            unsigned char* Xs = smem + W_SLOT + s * W_SLOT_BYTES;
-            unsigned char* Ls = Xs + 32768;
-            const int* ci_s = reinterpret_cast<const int*>(smem + W_CI + s * W_CI_BYTES);
-            const int* rp_s = reinterpret_cast<const int*>(smem + W_RP + s * W_RP_BYTES);
-            const float* bg_s = reinterpret_cast<const float*>(smem + W_BG + s * W_BG_BYTES);
-            const int tile0 = tile * TILE;
-            const int nrows = min(TILE, M - tile0);
-            const int ebase = single ? rp_s[0] : 0;
-            int inst = a.bv.tile_inst[tile];
-            mbar_wait_warp(bars + BAR_SP + s, par, lane);      // S' of this tile (PE-A runs a tile ahead)
-            WS_TICK(2)
-#pragma unroll 1
-            for (int it = 0; it < TILE / 32; ++it) {
-                const int rr = hw + 32 * it;
-                const bool valid = rr < nrows;
-                const size_t off = (size_t)(tile0 + (valid ? rr : 0)) * H + 4 * l;
-                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), iv = sv, rv = sv, ipo = sv, acc = sv;
-                if (valid && !(a.dbg & 4)) {              // own rows: in flight during the gather
-                    sv = ldg4_hint(a.y_in + off, pol_stream);
-                    iv = ldg4_hint(a.y_in + plane + off, pol_stream);
-                    rv = ldg4_hint(a.y_in + 2 * plane + off, pol_stream);
-                    ipo = ldg4_hint(a.ip_in + off, pol_keep);
-                }
-                if (single) {
-                    if (valid) {
-                        const int e_rel = rp_s[rr] - ebase, deg = (a.dbg & 2) ? 0 : rp_s[rr + 1] - rp_s[rr];
-                        if (e_rel + deg <= WS_CAP) {
-                            acc = gather_smem(lane_base, ci_s + e_rel, deg, pol_keep);
-                        } else {                          // hub tile: indices beyond the staged slice
-                            const GnInstance I = a.bv.inst[inst];
-                            for (int j = 0; j < deg; ++j) {
-                                const int c = I.colidx[ebase + e_rel + j] + I.row0;
-                                const float4 v = ldg4_hint(lane_base + (size_t)c * H, pol_keep);
-                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                } else {                                  // tile spans several (small) instances
-                    int row0 = 0, e0 = 0, deg = 0;
-                    const int32_t* ci = nullptr;
-                    if (valid) {
-                        const int g = tile0 + rr;
-                        while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
-                        const GnInstance I = a.bv.inst[inst];
-                        row0 = I.row0; ci = I.colidx;
-                        e0 = I.rowptr[g - row0];
-                        deg = I.rowptr[g - row0 + 1] - e0;
-                    }
-                    acc = gather_row(a.ip_in, ci, e0, deg, row0, l, lane);
-                }
-                float4 sn = make_float4(0.f, 0.f, 0.f, 0.f), in_ = sn, rn = sn;
-                if (valid) {
-                    const float4 sp = lds4(Ls, off0 + it * 4096);
-                    const float nbe = -bg_s[rr], ga = bg_s[TILE + rr], dt = a.dt;
-#define GN_COMP(c)                                                                  \
-    {                                                                               \
-        const float dS = __fmul_rn(nbe, __fmul_rn(acc.c, sp.c));                    \
-        const float dR = __fmul_rn(ga, ipo.c);                                      \
-        const float dI = __fsub_rn(-dS, dR);                                        \
-        sn.c = __fadd_rn(sv.c, __fmul_rn(dt, dS));                                  \
-        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
-        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
-    }
-                    GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
-#undef GN_COMP
-                    stg4_hint(a.y_out + off, sn, pol_stream);
-                    stg4_hint(a.y_out + plane + off, in_, pol_stream);
-                    stg4_hint(a.y_out + 2 * plane + off, rn, pol_stream);
-                    float4 hi, lo;
-                    umma::tf32_split4(in_, hi, lo);          // operand of GEMM2
-                    sts4(Xs, off0 + it * 4096, hi);
-                    sts4(Ls, off0 + it * 4096, lo);
-                }
-                if (a.probs != nullptr && !(a.dbg & 1))
-                    decode_row_bfly(sn, in_, rn, W3s, small, l, lane, valid, a.probs + (size_t)(tile0 + (valid ? rr : 0)) * 3);
-            }
-            umma::fence_proxy_async();
-            umma::mbar_arrive(bars + BAR_A2 + s);
-            WS_TICK(1)
-        }
-        if (a.tbuf && tid == 0) for (int i = 0; i < 3; ++i) atomicAdd((unsigned long long*)a.tbuf + i, (unsigned long long)tacc[i]);
-    } else {
-        // =============================== PE groups ===============================
-        const bool group_b = warp >= (WS_WORKERS + WS_PE) / 32;
-        const int ptid = (tid - WS_WORKERS) & (WS_PE - 1), pwarp = ptid >> 5;
-        const int bar_id = group_b ? 2 : 1;
-        const int poff0 = sw_off(ptid >> 4, ptid & 15);           // chunk (ptid&15) of rows (ptid>>4) + 8*i: + i KB
-        auto epilogue = [&](uint32_t acc_addr, unsigned char* dst) {
-            const int row = pwarp * 32 + lane;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[16];
-                umma::tmem_ld16(acc_addr + ((uint32_t)(pwarp * 32) << 16) + 16 * c, v);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c + 4 * j);
-                    float4 o;
-                    o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
-                    o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
-                    sts4(dst, sw_off(row, 4 * c + j), o);
-                }
-            }
-            umma::fence_before_sync();
-        };
-        if (!group_b) {
-            // -------- PE-A: operand preparation, GEMM1, S' epilogue
-            // The tile stream is fetched one tile ahead (meta[8..9]) so that the HBM -> L2 bulk prefetch of a
-            // tile's S / I / R / I' rows is issued a whole tile period before they are read.
-            auto fetch_next = [&](int k) {               // thread 0 only
-                const int seq = a.counter ? atomicAdd(a.counter, 1) : (int)blockIdx.x + k * (int)gridDim.x;
-                int tile = -1, single = 0;
-                if (seq < n_tiles) {
-                    tile = a.bv.tile_order[seq];
-                    const int t0 = tile * TILE, nr = min(TILE, M - t0);
-                    const GnInstance I = a.bv.inst[a.bv.tile_inst[tile]];
-                    single = (t0 + nr <= I.row0 + I.n) ? 1 : 0;
-                    if (!(a.dbg & 32)) {
-                        const uint32_t bytes = (uint32_t)nr * H * 4;
-                        prefetch_l2_bulk(a.y_in + (size_t)t0 * H, bytes);
-                        prefetch_l2_bulk(a.y_in + plane + (size_t)t0 * H, bytes);
-                        prefetch_l2_bulk(a.y_in + 2 * plane + (size_t)t0 * H, bytes);
-                        prefetch_l2_bulk_hint(a.ip_in + (size_t)t0 * H, bytes, pol_keep);
-                        const int ahead = t0 + I.n;     // same rows of the next instance (trial): I' for its gathers
-                        if (ahead < M) prefetch_l2_bulk_hint(a.ip_in + (size_t)ahead * H, (uint32_t)min(TILE, M - ahead) * H * 4, pol_keep);
-                    }
-                }
-                meta[8] = tile; meta[9] = single;
-            };
-            if (ptid == 0) fetch_next(0);
-            for (int k = 0;; ++k) {
-                const int s = k & 1;
-                const uint32_t par = (uint32_t)(k >> 1) & 1u;
-                unsigned char* Xs = smem + W_SLOT + s * W_SLOT_BYTES;
-                unsigned char* Ls = Xs + 32768;
-                int* ci_s = reinterpret_cast<int*>(smem + W_CI + s * W_CI_BYTES);
-                int* rp_s = reinterpret_cast<int*>(smem + W_RP + s * W_RP_BYTES);
-                float* bg_s = reinterpret_cast<float*>(smem + W_BG + s * W_BG_BYTES);
-                if (k >= 2) mbar_wait_warp(bars + BAR_FREE + s, par ^ 1u, lane);     // tile k-2 has left the slot
-                WS_TICK(0)
-                if (ptid == 0) { meta[4 * s] = meta[8]; meta[4 * s + 1] = meta[9]; }
-                umma::bar_sync(bar_id, WS_PE);
-                const int tile = __shfl_sync(0xffffffffu, meta[4 * s], 0);
-                if (tile < 0) {
-                    if (ptid == 0) umma::mbar_arrive(bars + BAR_CSR + s);
-                    break;
-                }
-                const bool single = __shfl_sync(0xffffffffu, meta[4 * s + 1], 0) != 0;
-                const int tile0 = tile * TILE, nrows = min(TILE, M - tile0);
-                const int inst0 = a.bv.tile_inst[tile];
-                const int i_row0 = a.bv.inst[inst0].row0;
-                const int32_t* rp = a.bv.inst[inst0].rowptr + (tile0 - i_row0);
-                // first wave of loads: CSR bounds, rowptr slice, beta/gamma, first half of the S rows
-                int e0 = 0, e1 = 0, rpv = 0, rp_last = 0;
-                float bev = 0.f, gav = 0.f;
-                if (single) {
-                    e0 = rp[0]; e1 = rp[nrows];
-                    if (ptid <= nrows) rpv = rp[ptid];
-                    if (ptid == 0 && nrows == TILE) rp_last = rp[TILE];
-                }
-                if (ptid < nrows) { bev = a.beta[tile0 + ptid]; gav = a.gamma[tile0 + ptid]; }
-                const float* src = a.y_in + (size_t)tile0 * H + (size_t)(ptid >> 4) * H + 4 * (ptid & 15);
-                float4 x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    x[i] = ((ptid >> 4) + 8 * i < nrows) ? ldg4(src + (size_t)(8 * i) * H) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ptid == 0) fetch_next(k + 1);        // atomic + prefetch issue overlap the loads above
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 hi, lo;
-                    umma::tf32_split4(x[i], hi, lo);
-                    sts4(Xs, poff0 + i * 1024, hi);
-                    sts4(Ls, poff0 + i * 1024, lo);
-                }
-                // second wave: second half of the S rows + the colidx slice (needs only e0 / e1)
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    x[i] = ((ptid >> 4) + 8 * (8 + i) < nrows) ? ldg4(src + (size_t)(8 * (8 + i)) * H) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (single) {
-                    const int ecnt = min(e1 - e0, WS_CAP);
-                    const int32_t* cg = a.bv.inst[inst0].colidx + e0;
-                    for (int j0 = ptid; j0 < ecnt; j0 += 8 * WS_PE) {
-                        int c[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) c[u] = (j0 + u * WS_PE < ecnt) ? cg[j0 + u * WS_PE] : 0;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) if (j0 + u * WS_PE < ecnt) ci_s[j0 + u * WS_PE] = c[u] + i_row0;
-                    }
-                    if (ptid <= nrows) rp_s[ptid] = rpv;
-                    if (ptid == 0 && nrows == TILE) rp_s[TILE] = rp_last;
-                }
-                if (ptid < nrows) { bg_s[ptid] = bev; bg_s[TILE + ptid] = gav; }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 hi, lo;
-                    umma::tf32_split4(x[i], hi, lo);
-                    sts4(Xs, poff0 + (8 + i) * 1024, hi);
-                    sts4(Ls, poff0 + (8 + i) * 1024, lo);
-                }
-                umma::fence_proxy_async();
-                umma::bar_sync(bar_id, WS_PE);
-                if (ptid == 0)
-                    umma::issue_split_gemm_to(tmem + s * 64, bars + BAR_M1 + s, whi, wlo, umma::smem_u32(Xs), umma::smem_u32(Ls));
-                umma::bar_sync(bar_id, WS_PE);
-                if (ptid == 0) umma::mbar_arrive(bars + BAR_CSR + s);          // workers may start gathering
-                WS_TICK(1)
-                mbar_wait_warp(bars + BAR_M1 + s, par, lane);
-                umma::fence_after_sync();
-                epilogue(tmem + s * 64, Ls);
-                umma::bar_sync(bar_id, WS_PE);
-                if (ptid == 0) umma::mbar_arrive(bars + BAR_SP + s);           // S' ready
-                WS_TICK(2)
-            }
-            if (a.tbuf && ptid == 0) for (int i = 0; i < 3; ++i) atomicAdd((unsigned long long*)a.tbuf + 3 + i, (unsigned long long)tacc[i]);
-        } else {
-            // -------- PE-B: GEMM2, I' epilogue, store
-            for (int k = 0;; ++k) {
-                const int s = k & 1;
-                const uint32_t par = (uint32_t)(k >> 1) & 1u;
-                unsigned char* Xs = smem + W_SLOT + s * W_SLOT_BYTES;
-                unsigned char* Ls = Xs + 32768;
-                mbar_wait_warp(bars + BAR_CSR + s, par, lane);                 // tile id of this slot is published
-                const int tile = __shfl_sync(0xffffffffu, meta[4 * s], 0);
-                if (tile < 0) break;
-                const int tile0 = tile * TILE, nrows = min(TILE, M - tile0);
-                mbar_wait_warp(bars + BAR_A2 + s, par, lane);                  // I_{k+1} operand tiles complete
-                WS_TICK(0)
-                if (ptid == 0)
-                    umma::issue_split_gemm_to(tmem + 128 + s * 64, bars + BAR_M2 + s, whi, wlo, umma::smem_u32(Xs), umma::smem_u32(Ls));
-                mbar_wait_warp(bars + BAR_M2 + s, par, lane);
-                umma::fence_after_sync();
-                epilogue(tmem + 128 + s * 64, Ls);
-                umma::bar_sync(bar_id, WS_PE);
-                float* dst = a.ip_out + (size_t)tile0 * H + (size_t)(ptid >> 4) * H + 4 * (ptid & 15);
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i)
-                    if ((ptid >> 4) + 8 * i < nrows) stg4_hint(dst + (size_t)(8 * i) * H, lds4(Ls, poff0 + i * 1024), pol_stream);
-                umma::bar_sync(bar_id, WS_PE);
-                if (ptid == 0) umma::mbar_arrive(bars + BAR_FREE + s);         // slot may be refilled
-                WS_TICK(1)
-            }
-            if (a.tbuf && ptid == 0) for (int i = 0; i < 2; ++i) atomicAdd((unsigned long long*)a.tbuf + 6 + i, (unsigned long long)tacc[i]);
-        }
-    }
-#undef WS_TICK
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 256);
-}
-
 // 0 = FFMA + accurate sigmoid ... 3 = tcgen05 + MUFU sigmoid; chosen by gnode_set_variant() / GNODE_VARIANT
 static int g_variant = -1;
-static long long* g_tbuf = nullptr;      // phase-timing accumulators of step_tc_kernel (GNODE_DBG bit 7)
+static long long* g_tbuf = nullptr;      // phase-timing accumulators of step_dual_kernel (GNODE_DBG bit 7)
 
 static int current_variant() {
     if (g_variant < 0) {
@@ -1726,32 +1013,6 @@ static int launch_step_v(const gnode_batch* b, const StepArgs& a, cudaStream_t s
     }
     const int grid = std::min(b->n_tiles, 2 * b->sm_count);
     step_kernel<MODE, VAR><<<grid, NTHREADS, SM_TOTAL, stream>>>(a);
-    GN_LAUNCH_CHECK();
-    return GNODE_OK;
-}
-
-template <bool FAST>
-static int launch_step_tc(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
-    static bool configured[64] = {false};
-    if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_tc_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_TOTAL));
-        configured[b->device & 63] = true;
-    }
-    const int grid = std::min(b->n_tiles, 2 * b->sm_count);
-    step_tc_kernel<FAST><<<grid, NTHREADS, T_TOTAL, stream>>>(a);
-    GN_LAUNCH_CHECK();
-    return GNODE_OK;
-}
-
-template <bool FAST>
-static int launch_step_ws(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
-    static bool configured[64] = {false};
-    if (!configured[b->device & 63]) {
-        GN_CUDA(cudaFuncSetAttribute(step_ws_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_TOTAL));
-        configured[b->device & 63] = true;
-    }
-    const int grid = std::min(b->n_tiles, b->sm_count);
-    step_ws_kernel<FAST><<<grid, WS_THREADS, W_TOTAL, stream>>>(a);
     GN_LAUNCH_CHECK();
     return GNODE_OK;
 }
@@ -1799,11 +1060,11 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
     return GNODE_OK;
 }
 
-// 3 = pipelined, 2 x 128-row tile pipelines per CTA (default; decoder hidden layer on the tensor core), 4 = the same
-// kernel with 4 x 64-row pipelines, 1 = phase-structured, 2 = warp-specialised, 0 = generic
+// 5 = pipelined kernel with the TMA-fed S stream (default), 6 = 5 without the deferred store wait, 3 = the same pipeline
+// with LDG-fed operands (round 1; also the fallback when no tensor map can be encoded), 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 9) : 5; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 6) : 5; }
     return g_step_kernel;
 }
 
@@ -1826,6 +1087,7 @@ static int persistent_choice() {
 }
 
 static bool persistent_forced() { return persistent_choice() == 1; }
+static int g_hub_relay = 1;
 
 // GNODE_DBG (timing experiments of the older step kernels) is read once per process
 static int debug_flags() {
@@ -1840,27 +1102,16 @@ template <int MODE>
 static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
     const int var = current_variant();
     if (MODE == MODE_STEP && use_dual()) {
-        if (step_kernel_choice() >= 5 && a.use_tma == 2) {      // TMA-fed S stream; 6 / 7 / 8: ablations of its two overlaps
+        if (step_kernel_choice() >= 5 && a.use_tma == 2) {      // TMA-fed S stream (6: without the deferred store wait)
             const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
 #define GN_SS(O) (fast ? (rf ? launch_step_stream<true, true, O>(b, a, stream) : launch_step_stream<true, false, O>(b, a, stream)) \
                        : (rf ? launch_step_stream<false, true, O>(b, a, stream) : launch_step_stream<false, false, O>(b, a, stream)))
-            switch (step_kernel_choice()) {
-                case 6: return GN_SS(0);
-                case 7: return GN_SS(1);
-                case 8: return GN_SS(2);
-                case 9: return GN_SS(7);
-                default: return GN_SS(3);
-            }
+            return step_kernel_choice() == 6 ? GN_SS(0) : GN_SS(1);
 #undef GN_SS
         }
-        if (step_kernel_choice() == 4) return (var & VAR_FASTSIG) ? launch_step_dual<true, 4, false>(b, a, stream) : launch_step_dual<false, 4, false>(b, a, stream);
         if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
         return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, false>(b, a, stream) : launch_step_dual<false, 2, false>(b, a, stream);
     }
-    if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 2)
-        return (var & VAR_FASTSIG) ? launch_step_ws<true>(b, a, stream) : launch_step_ws<false>(b, a, stream);
-    if (MODE == MODE_STEP && (var & VAR_TC) && step_kernel_choice() == 1)
-        return (var & VAR_FASTSIG) ? launch_step_tc<true>(b, a, stream) : launch_step_tc<false>(b, a, stream);
     switch (var) {
         case 0: return launch_step_v<MODE, 0>(b, a, stream);
         case 1: return launch_step_v<MODE, 1>(b, a, stream);
@@ -1912,7 +1163,7 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
-    if (kernel < 0 || kernel > 9) { set_error("gnode_set_step_kernel: kernel must be 0..9"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 6 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5 or 6"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }
@@ -1929,6 +1180,12 @@ extern "C" int gnode_set_persistent(int mode) {
     return GNODE_OK;
 }
 extern "C" int gnode_get_persistent(void) { return persistent_choice(); }
+extern "C" int gnode_set_hub_relay(int on) {
+    if (on < 0 || on > 1) { set_error("gnode_set_hub_relay: 0 or 1"); return GNODE_ERR_ARG; }
+    g_hub_relay = on;
+    return GNODE_OK;
+}
+extern "C" int gnode_get_hub_relay(void) { return g_hub_relay; }
 extern "C" int gnode_debug_phase_cycles(long long* out8) {
     if (!out8) return GNODE_ERR_ARG;
     for (int i = 0; i < 8; ++i) out8[i] = 0;
@@ -2031,6 +1288,7 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     a.probs = out(0); a.dt = 0.f;
     a.out_slot = nullptr; a.out_start = sel.start; a.out_stride = sel.stride; a.n_out = sel.n_out;
     a.dbg = debug_flags();
+    a.relay_off = g_hub_relay ? 0 : 1;
     a.tbuf = nullptr;
     if (a.dbg & 128) {
         if (!g_tbuf) { GN_CUDA(cudaMalloc(&g_tbuf, 64)); GN_CUDA(cudaMemset(g_tbuf, 0, 64)); }
@@ -2043,7 +1301,7 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     CUtensorMap tm_ip[2];
     const bool have_tma = dual && !(a.dbg & 32768) && encode_rows_map(&tm_ip[0], ip[0], M) && encode_rows_map(&tm_ip[1], ip[1], M);
     a.hid_i = dual ? hid_i : nullptr;
-    const bool rfree = dual && !traj && T > 1 && step_kernel_choice() != 4 && r_state_choice() == 1;
+    const bool rfree = dual && !traj && T > 1 && r_state_choice() == 1;
     a.hid_r = rfree ? hid_r : nullptr;
     rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;

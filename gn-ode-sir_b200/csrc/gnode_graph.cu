@@ -322,6 +322,8 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
 
 extern "C" int gnode_batch_destroy(gnode_batch_t b) {
     if (!b) return GNODE_OK;
+    for (auto& e : b->bwd_graphs) cudaGraphExecDestroy((cudaGraphExec_t)e.exec);
+    if (b->capture_stream) cudaStreamDestroy((cudaStream_t)b->capture_stream);
     cudaFree(b->d_inst);
     cudaFree(b->d_tile_inst);
     cudaFree(b->d_tile_order);

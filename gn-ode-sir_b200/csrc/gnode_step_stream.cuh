@@ -6,16 +6,18 @@
 //     32 x 128 fp32, SASS UTMALDG) issued by the otherwise idle metadata thread as soon as GEMM2 of the current tile
 //     has finished reading the operand buffer: no registers, no LSU wavefronts and no L1 lines for this stream, and the
 //     load's latency hides behind the I' epilogue and the tile turn-over;
-//   * the tile lands directly in the canonical UMMA K-major operand layout and the RAW fp32 tile is the `hi` operand:
-//     tcgen05.mma kind::tf32 reads the top 19 bits of each 32-bit element, i.e. hi = trunc_tf32(x) implicitly, and the
-//     threads only write lo = rna_tf32(x - trunc_tf32(x)). The raw tile stays in shared memory until the row update
-//     reads S_k from it: S_k is read from HBM/L2 ONCE per step (step_dual_kernel: twice);
+//   * the tile lands directly in the canonical UMMA K-major operand layout and BECOMES the `hi` operand in place:
+//     tcgen05.mma kind::tf32 reads only the top 19 bits of each 32-bit element, so a word whose top bits are
+//     rna_tf32(x) and whose low 13 bits are those of x is hi to the tensor core and still x (exactly) to the row update
+//     that reads S_k from it later (tf32_pack / tf32_unpack): S_k is read from HBM/L2 ONCE per step (step_dual_kernel:
+//     twice), and the split product is bitwise the LDG-fed kernel's;
 //   * the neighbour sum is folded into S' in place (AI * S', the first product of dS, ode_nn_ngraph_sim.py:75), so the
 //     parked value needs no buffer of its own. (Measured and rejected: the gathering half-warp performing the whole row
 //     update with its own I_k / I'_k rows requested together with the neighbour rows -- 1.64e9 vs 1.66e9 node-steps/s,
-//     profiles/r2b_ab_step_kernels.log.)
+//     profiles/r2b_ab_step_kernels.log; the first row pair gathered while GEMM1 runs -- 1.667e9 vs 1.683e9; the own rows
+//     of the first update pass requested before the barrier -- 1.687e9 vs 1.683e9, noise; profiles/r2d_ab_stream_overlaps.log.)
 // Arithmetic of the update is the reference's, op for op; S, I, R and the probabilities are bitwise
-// those of step_dual_kernel except for the A-operand split (truncated hi: per-product error 1.5 * 2^-22 instead of 2^-22).
+// those of step_dual_kernel.
 #pragma once
 
 namespace gnode {
@@ -53,14 +55,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// lo part of the A operand when the raw fp32 value is the hi operand: the tensor core uses the top 19 bits
-// (sign, 8 exponent, 10 mantissa bits); the residual is exact in fp32 and rounded to tf32
-__device__ __forceinline__ float tf32_lo_of_raw(float x) {
-    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    return umma::tf32_rna(x - hi);
+// The fp32 tile that the TMA delivered is turned into the hi operand IN PLACE without losing the fp32 value: the tensor
+// core reads only the top 19 bits of an element (tools/umma_lowbits_probe.cu: the low 13 mantissa bits are ignored,
+// i.e. truncation), so the word  p = bits(rna_tf32(x)) | (bits(x) & 0x1FFF)  is seen by tcgen05.mma as hi = rna_tf32(x)
+// -- the same hi as a separate operand tile would hold -- while x is recovered exactly as
+// bits(x) = p - ((p & 0x1000) << 1)  (rounding up happened iff bit 12 of x is set; it added 0x2000 to the pattern).
+// lo = rna_tf32(x - hi) as in the LDG-fed kernel: the split product is bitwise the same.
+__device__ __forceinline__ float tf32_pack(float x, float& lo) {
+    const float hi = umma::tf32_rna(x);
+    lo = umma::tf32_rna(x - hi);
+    return __uint_as_float(__float_as_uint(hi) | (__float_as_uint(x) & 0x1FFFu));
 }
-__device__ __forceinline__ float4 tf32_lo_of_raw4(float4 x) {
-    return make_float4(tf32_lo_of_raw(x.x), tf32_lo_of_raw(x.y), tf32_lo_of_raw(x.z), tf32_lo_of_raw(x.w));
+__device__ __forceinline__ float tf32_unpack(float p) {
+    const uint32_t b = __float_as_uint(p);
+    return __uint_as_float(b - ((b & 0x1000u) << 1));
+}
+__device__ __forceinline__ float4 tf32_pack4(float4 x, float4& lo) {
+    return make_float4(tf32_pack(x.x, lo.x), tf32_pack(x.y, lo.y), tf32_pack(x.z, lo.z), tf32_pack(x.w, lo.w));
+}
+__device__ __forceinline__ float4 tf32_unpack4(float4 p) {
+    return make_float4(tf32_unpack(p.x), tf32_unpack(p.y), tf32_unpack(p.z), tf32_unpack(p.w));
 }
 
 // neighbour sum specialised by the pair's larger degree: 1..MAXR rows in one round trip, longer rows in rounds of 8
@@ -99,7 +113,7 @@ struct SStep {
     float dt;
 };
 
-template <bool FAST, bool PERSIST, bool RF, int OPT>      // OPT bit 0: first gather overlaps GEMM1, bit 1: first own-row loads cross the barrier
+template <bool FAST, bool PERSIST, bool RF, int OPT>      // OPT bit 0: no block barrier after the I' store (see P5)
 __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_constant__ StepArgs a) {
     using C = StreamCfg;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
 
     umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
     if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
-    if (t == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(sbar, (OPT & 4) ? 2 : 1); }
+    if (t == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(sbar, (OPT & 1) ? 2 : 1); }
     umma::fence_before_sync();
     if (tid < H) bs[tid] = a.p.lin_b[tid];
     if (tid < 4 * H) W3s[tid] = a.p.l3_w[tid];
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         fetch_meta(0);
         if (PERSIST) asm volatile("fence.proxy.async;" ::: "memory");   // state rows written by other SMs (generic proxy) -> TMA reads
         issue_s_load();
-        if ((OPT & 4) && meta->seq < n_tiles) umma::mbar_arrive(sbar);   // second arrival: Ls is free (no TMA store pending)
+        if ((OPT & 1) && meta->seq < n_tiles) umma::mbar_arrive(sbar);   // second arrival: Ls is free (no TMA store pending)
     }
     kfetch = 1;
     HSYNC();
@@ -232,7 +246,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         if (m.seq >= n_tiles) break;
         const int tile0 = m.tile0, nrows = m.nrows, i_row0 = m.i_row0, ebase = m.ebase;
         const bool single = (m.single & 1) != 0;
-        const bool relay = (m.single & 2) != 0;                       // the tile has isolated hub rows (host cost model)
+        const bool relay = (m.single & 2) != 0 && !a.relay_off;       // the tile has isolated hub rows (host cost model)
         const float dt = STP(dt);
 
         // ---- P1: CSR slice, beta/gamma -> smem; lo operand of the TMA-loaded S_k tile
@@ -249,7 +263,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
             umma::mbar_wait(sbar, sphase); sphase ^= 1;               // the S_k tile has landed in Xs
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sts4(Ls, off0 + i * PASS, tf32_lo_of_raw4(lds4(Xs, off0 + i * PASS)));
+            for (int i = 0; i < 4; ++i) {
+                float4 lo;
+                const float4 pk = tf32_pack4(lds4(Xs, off0 + i * PASS), lo);
+                sts4(Xs, off0 + i * PASS, pk);
+                sts4(Ls, off0 + i * PASS, lo);
+            }
             umma::fence_proxy_async();
             if (t == 0) *row_ctr = 0;
             if (t < TR / 32) hub_mask[t] = 0u;
@@ -289,14 +308,6 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 return gather_smem_zm<12>(lane_base, m.colidx + ebase + e_rel, deg, zrow, pol_keep);
             return gather_smem_zm<12>(lane_base, ci_s + e_rel, deg, zrow, pol_keep);
         };
-        // The gather needs nothing of GEMM1 (only folding AI into S' does): the first row pair's neighbour rows are
-        // fetched and summed WHILE the tensor core runs, which hides the GEMM and its completion latency behind one
-        // memory round trip (ordinary single-instance tiles; relay tiles first have to publish their hub mask)
-        const bool early = (OPT & 1) && single && !relay;
-        int p_e = 0, rr_e = 0;
-        bool ok_e = false;
-        float4 acc_e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (early) { p_e = draw_pair(); if (p_e < TR / 2) acc_e = gather_pair(p_e, rr_e, ok_e); }
         umma::mbar_wait_suspend(mbar, phase); phase ^= 1;
         umma::fence_after_sync();
         {
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (ok) {
                 const int o = C::sw(rr, l);
                 const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                const float4 s = lds4(Xs, o);
+                const float4 s = tf32_unpack4(lds4(Xs, o));
                 const float nbe = -bg_s[rr], ga = bg_s[TR + rr];
                 float4 sn, in_, rn;
 #define GN_COMP(c)                                                                  \
@@ -355,8 +366,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 stg4_hint(STP(y_out) + off, sn, pol_stream);
                 stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
                 if (!RF) stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
-                sts4(Xs, o, in_);                                    // raw = hi operand of GEMM2
-                sts4(Ls, o, tf32_lo_of_raw4(in_));
+                float4 ilo;
+                sts4(Xs, o, tf32_pack4(in_, ilo));                   // hi operand of GEMM2 (packed like the S tile)
+                sts4(Ls, o, ilo);
                 if (dec) {
                     const float4 dv = RF ? ipo : rv;
                     hv[0] = dot4(dv, w30); hv[1] = dot4(dv, w31); hv[2] = dot4(dv, w32); hv[3] = dot4(dv, w33);
@@ -385,11 +397,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         // ---- P3a: neighbour sums AI (sequential, ascending columns), folded into S' in place
         {
             if (single) {
-                int p;
-                if (early) {
-                    if (p_e < TR / 2) finish_row(rr_e, ok_e, acc_e);
-                    p = p_e < TR / 2 ? draw_pair() : p_e;
-                } else p = draw_pair();
+                int p = draw_pair();
                 while (p < TR / 2) {
                     int rr; bool ok;
                     const float4 acc = gather_pair(p, rr, ok);
@@ -475,16 +483,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
         }
         {
-            // the own rows of the first pass are requested BEFORE the barrier: their latency overlaps the wait for the
-            // slowest gathering warp
-            float4 iv, rv, ipo;
-            if (OPT & 2) load_own(hw, hw < nrows, iv, rv, ipo);
             HSYNC();                                                            // S2b: every AI * S' row is parked
             // ---- P3b: SIR update (own I_k / I'_k rows one pass ahead in registers; S_k from the raw operand tile; the
             //      lane's 4 x 4 linear3 weights stay in registers for the four passes)
             const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),
                          w32 = lds4((const unsigned char*)W3s, 512 + 16 * l), w33 = lds4((const unsigned char*)W3s, 768 + 16 * l);
-            if (!(OPT & 2)) load_own(hw, hw < nrows, iv, rv, ipo);
+            float4 iv, rv, ipo;
+            load_own(hw, hw < nrows, iv, rv, ipo);
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
                 const int rr = hw + RSTEP * it;
@@ -556,12 +561,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             tma_store_2d(STP_TM(), Ls + C::KBLK, 32, tile0, pol_stream);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            // OPT bit 2: no block barrier here. The staged tile may be overwritten once the bulk group has read it; the next
+            // OPT bit 0: no block barrier here. The staged tile may be overwritten once the bulk group has read it; the next
             // tile's threads learn that through the S-load mbarrier, whose second arrival is this thread's (they wait on
             // it before their first write to Ls), so the store's read time overlaps the S load and the CSR staging.
-            if ((OPT & 4) && meta->seq < n_tiles) umma::mbar_arrive(sbar);
+            if ((OPT & 1) && meta->seq < n_tiles) umma::mbar_arrive(sbar);
         }
-        if (!(OPT & 4)) HSYNC();                                                // S5
+        if (!(OPT & 1)) HSYNC();                                                // S5
     }
     if (step + 1 < n_steps) {
         if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

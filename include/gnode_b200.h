@@ -79,10 +79,11 @@ int gnode_get_variant(void);
 /* Structure of the tensor-core step kernel (variants with bit 0 set): 5 = pipelined, S_k stream by TMA (default: one
  * 1024-thread CTA per SM running two 128-row tile pipelines that share the weight operand; the S_k tile arrives by TMA
  * tensor loads straight into the UMMA operand layout, the raw fp32 tile is the hi operand and S_k is read once; the
- * decoder's hidden layer comes out of the step's two GEMMs), 3 = the same pipeline with LDG-fed operands (round 1),
- * 4 = 3 with four 64-row pipelines, 1 = phase-structured (two 512-thread CTAs per SM), 2 = warp-specialised,
- * 0 = generic. Default: env GNODE_STEP_KERNEL or 5. All produce the same trajectories
- * within the parity tolerance. */
+ * decoder's hidden layer comes out of the step's two GEMMs), 6 = 5 with a block barrier after the I' store, 3 = the same
+ * pipeline with LDG-fed operands (round 1; also what runs when no tensor map can be encoded), 0 = generic.
+ * Default: env GNODE_STEP_KERNEL or 5. All produce the same trajectories within the parity tolerance.
+ * These switches (variant, step kernel, R state, persistent) are PROCESS-WIDE settings read at every rollout call:
+ * set them before launching work from several threads, not concurrently with it. */
 int gnode_set_step_kernel(int kernel);
 int gnode_get_step_kernel(void);
 /* How inference rollouts (traj == NULL, default step kernel) carry the R block. 1 (default) = as its four linear3
@@ -98,6 +99,10 @@ int gnode_get_r_state(void);
  * Env GNODE_PERSISTENT=0/1 sets the initial value. Process-wide, like the other switches here. */
 int gnode_set_persistent(int mode);
 int gnode_get_persistent(void);
+/* In-order relay for isolated hub rows (degree > 512): 1 (default) = on, 0 = every row is walked by one
+ * half-warp. Both give BITWISE the same sums; the switch exists for that check and for A/B measurements. */
+int gnode_set_hub_relay(int on);
+int gnode_get_hub_relay(void);
 /* debug: per-phase SM-cycle sums of the step kernel collected while env GNODE_DBG has bit 7 set; resets them */
 int gnode_debug_phase_cycles(long long* out8);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */

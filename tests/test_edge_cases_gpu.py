@@ -58,7 +58,7 @@ def test_directed_graph_rollout(gn):
 
 def test_bench_graph_kernel_structures_agree(gn):
     """Full-size epinions stand-in (BA N=75,879: hub tiles, slice overflow, partial last tile), 3 trials: the pipelined
-    tensor-core kernel (2 x 128 and 4 x 64 rows) against the generic fp32 FFMA kernel that the goldens validate."""
+    tensor-core kernels (TMA-fed and LDG-fed operands) against the generic fp32 FFMA kernel that the goldens validate."""
     from gn_ode_sir_b200 import _lib, synth
     L = _lib.lib()
     A = synth.epinions_standin(0)
@@ -71,14 +71,14 @@ def test_bench_graph_kernel_structures_agree(gn):
     prev_k, prev_v = L.gnode_get_step_kernel(), L.gnode_get_variant()
     out = {}
     try:
-        for name, kern, var in (("dual", 3, 3), ("quad", 4, 3), ("ffma", 0, 0)):
+        for name, kern, var in (("stream", 5, 3), ("dual", 3, 3), ("ffma", 0, 0)):
             _lib.check(L.gnode_set_step_kernel(kern), "set_step_kernel")
             _lib.check(L.gnode_set_variant(var), "set_variant")
             with torch.no_grad():
                 out[name] = gn.rollout.rollout(x, batch, dt, params).cpu()
     finally:
         L.gnode_set_step_kernel(prev_k); L.gnode_set_variant(prev_v)
-    for name in ("dual", "quad"):
+    for name in ("stream", "dual"):
         err = (out[name] - out["ffma"]).abs().max().item()
         print("%s vs fp32 FFMA kernel on the bench graph: %.3e" % (name, err))
         assert err < 5e-6, (name, err)
@@ -110,9 +110,10 @@ def test_bench_size_batch_against_oracle(gn):
     assert err < 1e-5, err
 
 
-def test_hub_relay_is_bitwise_the_serial_walk(gn, monkeypatch):
+@pytest.mark.parametrize("kernel", [5, 3], ids=["stream", "dual"])
+def test_hub_relay_is_bitwise_the_serial_walk(gn, kernel):
     """Rows longer than 512 neighbours are loaded by the whole tile pipeline and added by an in-order relay; the
-    result must be BITWISE the serial ascending-column walk (GNODE_DBG bit 22 switches the relay off), for isolated
+    result must be BITWISE the serial ascending-column walk (gnode_set_hub_relay(0) switches the relay off), for isolated
     hubs in different tiles, several hubs in one tile, a hub at degree 513 (just above the threshold) and one at 512
     (just below), with batches in the persistent and in the launch-per-step regime."""
     import networkx as nx
@@ -129,18 +130,27 @@ def test_hub_relay_is_bitwise_the_serial_walk(gn, monkeypatch):
     A.sort_indices()
     deg = np.diff(A.indptr)
     assert (deg > 512).sum() >= 5 and deg.max() > 2400
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
     params = dev_params(orc.default_params(64, seed=4))
     graph = gn.DeviceGraph(A)
     dt = gn.rollout.dt_array(orc.time_grid(20, 0.5))
-    for B in (2, 120):                         # 94 tiles (persistent rollout) / 5625 tiles (one launch per step)
-        x = torch.cat([orc.synthetic_trial(N, 64, 40 + b) for b in range(B)]).to(DEV)
-        batch = gn.DeviceBatch([graph] * B)
-        monkeypatch.delenv("GNODE_DBG", raising=False)
-        with torch.no_grad():
-            relay = gn.rollout.rollout(x, batch, dt, params)
-        monkeypatch.setenv("GNODE_DBG", str(1 << 22))
-        with torch.no_grad():
-            serial = gn.rollout.rollout(x, batch, dt, params)
-        monkeypatch.delenv("GNODE_DBG", raising=False)
-        assert torch.equal(relay, serial), (B, (relay - serial).abs().max().item())
-        assert torch.isfinite(relay).all()
+    prev_k = L.gnode_get_step_kernel()
+    try:
+        _lib.check(L.gnode_set_step_kernel(kernel), "gnode_set_step_kernel")
+        for B in (2, 120):                         # 94 tiles (persistent rollout) / 5625 tiles (one launch per step)
+            x = torch.cat([orc.synthetic_trial(N, 64, 40 + b) for b in range(B)]).to(DEV)
+            batch = gn.DeviceBatch([graph] * B)
+            assert L.gnode_set_hub_relay(1) == 0 and L.gnode_get_hub_relay() == 1
+            with torch.no_grad():
+                relay = gn.rollout.rollout(x, batch, dt, params)
+            assert L.gnode_set_hub_relay(0) == 0
+            with torch.no_grad():
+                serial = gn.rollout.rollout(x, batch, dt, params)
+            assert torch.equal(relay, serial), (B, (relay - serial).abs().max().item())
+            assert torch.isfinite(relay).all()
+    finally:
+        L.gnode_set_hub_relay(1)
+        L.gnode_set_step_kernel(prev_k)
+    # and the relay path itself against the CPU oracle's strictly sequential sum: S' * AI of a hub row after ONE step is
+    # exercised by tests/test_parity_gpu.py::test_rollout_large_graph_against_fp64[sim_wikivote_b2] (max degree 1065)
