@@ -45,6 +45,7 @@ struct BwdArgs {
     const float* gP;               // [M][3] dL/dprobs at time j (may be null: no decoder term)
     float* a;                      // [3][M][H] adjoint (in place)
     float* Sp; float* Ip; float* AI; float* G;   // [M][H] scratch
+    const float* Ipf; const float* AIf;          // [M][H] I'_j and AI_j = A I'_j kept by the forward (auxiliary storage), or null
     float* part;                   // per-block partial sums of this kernel family
     float dt;
     int only_dec;                  // 1: only a += D(y, gP)
@@ -88,6 +89,67 @@ __global__ void __launch_bounds__(NTHREADS, 2) bwd_transform_kernel(const BwdArg
             store_tile(comp == 0 ? a.Sp : a.Ip, Os, tile0, M, tid);
             __syncthreads();
         }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- K1' (auxiliary storage)
+// With I'_j and AI_j kept by the forward, everything that depends on S' alone leaves this tile kernel directly:
+//   G = gAI = beta (aI - aS) S'  -> G      gzS = beta (aI - aS) AI S'(1 - S')  -> Sp
+// (bwd_row_kernel's gather of A I' and the S' round trip through HBM are gone; I' is not recomputed.)
+__global__ void __launch_bounds__(NTHREADS, 2) bwd_transform_g_kernel(const BwdArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Xs = smem + K1_SM_X;
+    unsigned char* Os = smem + K1_SM_O;
+    float* bs = reinterpret_cast<float*>(smem + K1_SM_B);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + K1_SM_BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + K1_SM_BAR + 8);
+    const int tid = threadIdx.x;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    umma::prepare_weights(a.p.lin_w, smem + K1_SM_WHI, smem + K1_SM_WLO, tid, NTHREADS);
+    if (tid < 32) umma::tmem_alloc(tslot, umma::TMEM_COLS);
+    if (tid == 0) umma::mbar_init(mbar, 1);
+    umma::fence_before_sync();
+    if (tid < H) bs[tid] = a.p.lin_b[tid];
+    __syncthreads();
+    umma::fence_after_sync();
+    umma::Ctx cx;
+    cx.tmem = *tslot; cx.bar = mbar; cx.phase = 0;
+    cx.whi = umma::smem_u32(smem + K1_SM_WHI); cx.wlo = umma::smem_u32(smem + K1_SM_WLO);
+    for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TILE;
+        load_tile(Xs, a.y, tile0, M, tid);
+        __syncthreads();
+        umma::gemm_sigmoid_tc<false>(cx, Xs, Os, bs, tid);      // Xs -> tf32 hi, Os: lo, then S'
+        __syncthreads();
+#pragma unroll 2
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * NTHREADS;
+            const int rr = idx >> 4, c4 = idx & 15;
+            const int64_t g = tile0 + rr;
+            if (g < M) {
+                const size_t off = (size_t)g * H + 4 * c4;
+                const float4 aS = ldg4(a.a + off), aI = ldg4(a.a + plane + off), ai = ldg4_stream(a.AIf + off);
+                const float be = a.x[(size_t)g * a.ldx + 3];
+                const float4 sp = lds4(Os, sw_off(rr, c4));
+                float4 G, gz;
+#define GN_G(c)                                                     \
+    {                                                               \
+        const float q = aI.c - aS.c;                                \
+        G.c = be * q * sp.c;                                        \
+        gz.c = be * q * ai.c * sp.c * (1.0f - sp.c);                \
+    }
+                GN_G(x) GN_G(y) GN_G(z) GN_G(w)
+#undef GN_G
+                stg4(a.G + off, G);
+                stg4(a.Sp + off, gz);
+            }
+        }
+        __syncthreads();
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -260,6 +322,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a
 //   gzI = (A^T gAI + gamma (aR - aI)) I'(1-I')      gzS = beta (aI - aS) AI S'(1-S')
 // written IN PLACE over the row's own S' (Sp <- gzS) and AI (AI <- gzI): both are read only by this row's threads.
 // Separate from the tile kernel so that this latency-bound gather runs at row-kernel occupancy.
+template <bool AUX>       // AUX: gzS was written by bwd_transform_g_kernel; I' comes from the forward's auxiliary storage
 __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_gz_kernel(const BwdArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, l = tid & 15, hw = tid >> 4;
     const int M = a.bv.M;
@@ -275,8 +338,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_gz_kernel(const BwdArgs a)
         float be = 0.f, ga = 0.f;
         float4 aS, aI, aR, sp, ip, ai;
         if (valid) {
-            aS = ldg4(a.a + off); aI = ldg4(a.a + plane + off); aR = ldg4(a.a + 2 * plane + off);
-            sp = ldg4(a.Sp + off); ip = ldg4_stream(a.Ip + off); ai = ldg4(a.AI + off);
+            aI = ldg4(a.a + plane + off); aR = ldg4(a.a + 2 * plane + off);
+            if (AUX) {
+                ip = ldg4_stream(a.Ipf + off);
+                aS = aI; sp = ip; ai = ip;                     // unused
+            } else {
+                aS = ldg4(a.a + off);
+                sp = ldg4(a.Sp + off); ip = ldg4_stream(a.Ip + off); ai = ldg4(a.AI + off);
+            }
             int inst = a.bv.tile_inst[g / TILE];
             while (inst + 1 < a.bv.n_inst && a.bv.inst[inst + 1].row0 <= g) ++inst;
             const GnInstance I = a.bv.inst[inst];
@@ -299,7 +368,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_gz_kernel(const BwdArgs a)
     }
             GN_GZ(x) GN_GZ(y) GN_GZ(z) GN_GZ(w)
 #undef GN_GZ
-            stg4(a.Sp + off, gzs);
+            if (!AUX) stg4(a.Sp + off, gzs);
             stg4(a.AI + off, gzi);
         }
     }
@@ -519,26 +588,33 @@ __global__ void __launch_bounds__(K3B_THREADS, 2) bwd_vjp2_kernel(const BwdArgs 
     const uint32_t wthi = umma::smem_u32(smem + K3B_SM_WTHI), wtlo = umma::smem_u32(smem + K3B_SM_WTLO);
     uint32_t phase = 0;
 
+    // gz tile (written by bwd_gz_kernel / bwd_transform_g_kernel over Sp / AI) and the state tile of one (tile, part)
+    // unit -> shared memory, asynchronously: the request for the NEXT unit is issued as soon as the GEMM has consumed
+    // the current tiles, so that its latency hides behind the read-modify-write of the adjoint
+    auto request_unit = [&](int tile, int part) {
+        if (tile >= a.bv.n_tiles) return;
+        const int64_t tile0 = (int64_t)tile * TILE;
+        const float* gsrc = part == 0 ? a.Sp : a.AI;
+        const float* xsrc = a.y + (size_t)part * plane;
+        for (int idx = tid; idx < TILE * CHUNKS; idx += K3B_THREADS) {
+            const int rr = idx >> 4, c4 = idx & 15;
+            const int64_t g = tile0 + rr;
+            const int so = sw_off(rr, c4);
+            if (g < M) {
+                const size_t go = (size_t)g * H + 4 * c4;
+                cp_async16(G + so, gsrc + go);
+                cp_async16(X + so, xsrc + go);
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                sts4(G, so, z); sts4(X, so, z);
+            }
+        }
+    };
+    request_unit(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < a.bv.n_tiles; tile += gridDim.x) {
         const int64_t tile0 = (int64_t)tile * TILE;
 #pragma unroll 1
         for (int part = 0; part < 2; ++part) {
-            // gz tile (written by bwd_gz_kernel over Sp / AI) and the state tile of this part -> shared memory
-            const float* gsrc = part == 0 ? a.Sp : a.AI;
-            const float* xsrc = a.y + (size_t)part * plane;
-            for (int idx = tid; idx < TILE * CHUNKS; idx += K3B_THREADS) {
-                const int rr = idx >> 4, c4 = idx & 15;
-                const int64_t g = tile0 + rr;
-                const int so = sw_off(rr, c4);
-                if (g < M) {
-                    const size_t go = (size_t)g * H + 4 * c4;
-                    cp_async16(G + so, gsrc + go);
-                    cp_async16(X + so, xsrc + go);
-                } else {
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    sts4(G, so, z); sts4(X, so, z);
-                }
-            }
             cp_async_wait_all();
             __syncthreads();
             // ---- vW[h][j] += sum_r gz[r][h] x[r][j] ; vb[h] += sum_r gz[r][h]   (fp32 FFMA)
@@ -576,6 +652,9 @@ __global__ void __launch_bounds__(K3B_THREADS, 2) bwd_vjp2_kernel(const BwdArgs 
             umma::mbar_wait(mbar, phase);
             phase ^= 1;
             umma::fence_after_sync();
+            // the tensor core has read both tiles: the next unit may land there (generic-proxy writes after the async
+            // proxy's reads are ordered by the mbarrier wait above)
+            request_unit(part == 0 ? tile : tile + (int)gridDim.x, part ^ 1);
             // ---- a[part] += dt * v: warp (q = lane quarter, ch = 32-column half), thread = tile row (vR = 0)
             {
                 const int q = warp & 3, ch = warp >> 2;
@@ -718,7 +797,7 @@ extern "C" int gnode_rollout_backward(gnode_batch_t b, const float* x, int64_t l
                                       int32_t T, const float* dt_host, const float* traj, const float* grad_probs,
                                       int32_t grad_mode, float* grads_out, void* workspace, size_t workspace_bytes,
                                       void* stream_) {
-    return gnode_rollout_backward_sel(b, x, ldx, p, T, dt_host, traj, grad_probs, nullptr, 0, grad_mode, grads_out,
+    return gnode_rollout_backward_aux(b, x, ldx, p, T, dt_host, traj, nullptr, grad_probs, nullptr, 0, grad_mode, grads_out,
                                       workspace, workspace_bytes, stream_);
 }
 
@@ -726,6 +805,15 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
                                           int32_t T, const float* dt_host, const float* traj, const float* grad_probs,
                                           const int32_t* out_steps, int32_t n_out, int32_t grad_mode, float* grads_out,
                                           void* workspace, size_t workspace_bytes, void* stream_) {
+    return gnode_rollout_backward_aux(b, x, ldx, p, T, dt_host, traj, nullptr, grad_probs, out_steps, n_out, grad_mode,
+                                      grads_out, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int gnode_rollout_backward_aux(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                          int32_t T, const float* dt_host, const float* traj, const float* aux,
+                                          const float* grad_probs, const int32_t* out_steps, int32_t n_out,
+                                          int32_t grad_mode, float* grads_out, void* workspace, size_t workspace_bytes,
+                                          void* stream_) {
     if (!b || !x || !p || !traj || !grad_probs || !grads_out || !workspace || T < 1 || ldx < 5 ||
         (T > 1 && !dt_host) || (grad_mode != GNODE_GRAD_ADJOINT && grad_mode != GNODE_GRAD_DISCRETE)) {
         set_error("gnode_rollout_backward: bad arguments (T=%d ldx=%lld grad_mode=%d)", T, (long long)ldx, grad_mode);
@@ -744,6 +832,7 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
     static bool configured[64] = {false};
     if (!configured[b->device & 63]) {
         GN_CUDA(cudaFuncSetAttribute(bwd_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SM_TOTAL));
+        GN_CUDA(cudaFuncSetAttribute(bwd_transform_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SM_TOTAL));
         GN_CUDA(cudaFuncSetAttribute(bwd_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SM_TOTAL));
         GN_CUDA(cudaFuncSetAttribute(bwd_vjp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3B_SM_TOTAL));
         configured[b->device & 63] = true;
@@ -766,7 +855,7 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
                 if (key == 0) key = 1469598103934665603ull;
                 for (size_t i = 0; i < n; ++i) { key ^= c[i]; key *= 1099511628211ull; }
             };
-            const void* ptrs[] = {x, traj, grad_probs, grads_out, workspace, stream_};
+            const void* ptrs[] = {x, traj, aux, grad_probs, grads_out, workspace, stream_};
             mix(ptrs, sizeof(ptrs)); mix(p, sizeof(*p)); mix(&ldx, sizeof(ldx)); mix(&T, sizeof(T));
             mix(&grad_mode, sizeof(grad_mode)); mix(dt_host, sizeof(float) * (size_t)(T > 1 ? T - 1 : 0));
             mix(sel.slot.data(), sizeof(int) * sel.slot.size());
@@ -818,7 +907,25 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
         GN_LAUNCH_CHECK();
         return GNODE_OK;
     };
+    // auxiliary storage of the forward (gnode_rollout_forward_aux): aux[k][0] = I'_k (all k), aux[k][1] = A I'_k (k <= T-2)
+    const size_t Mr = (M + TILE - 1) / TILE * TILE, aux_plane = (Mr + 1) * H;
+    a.Ipf = nullptr; a.AIf = nullptr;
     auto vjp_step = [&](int j, float dt, bool with_decoder) -> int {
+        if (aux && j <= T - 2) {
+            // three launches, one neighbour gather: a += D(y_j, gP_j) ; S' -> (G, gzS) ; A^T G -> gzI ; tile kernel
+            if (with_decoder) { const int rc2 = dec_only(j); if (rc2) return rc2; }
+            a.y = state(j); a.gP = nullptr; a.dt = dt; a.only_dec = 0; a.part = nullptr;
+            a.Ipf = aux + (size_t)j * 2 * aux_plane; a.AIf = a.Ipf + aux_plane;
+            bwd_transform_g_kernel<<<pl.grid_tile1, NTHREADS, K1_SM_TOTAL, stream>>>(a);
+            GN_LAUNCH_CHECK();
+            bwd_gz_kernel<true><<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+            GN_LAUNCH_CHECK();
+            a.part = plin;
+            if (vjp_kernel_choice() == 2) bwd_vjp2_kernel<<<pl.grid_tile3, K3B_THREADS, K3B_SM_TOTAL, stream>>>(a);
+            else bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
+            GN_LAUNCH_CHECK();
+            return GNODE_OK;
+        }
         a.y = state(j); a.gP = with_decoder ? gp(j) : nullptr; a.dt = dt; a.only_dec = 0;
         a.part = nullptr;
         bwd_transform_kernel<<<pl.grid_tile1, NTHREADS, K1_SM_TOTAL, stream>>>(a);
@@ -827,7 +934,7 @@ extern "C" int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64
         bwd_row_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
         a.part = nullptr;
-        bwd_gz_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+        bwd_gz_kernel<false><<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
         a.part = plin;
         if (vjp_kernel_choice() == 2) bwd_vjp2_kernel<<<pl.grid_tile3, K3B_THREADS, K3B_SM_TOTAL, stream>>>(a);

@@ -63,6 +63,12 @@ struct StepArgs {
     const int* out_slot;  // [T] output slot of every grid point (-1: not emitted), or null: slot(k) = (k - out_start) / out_stride
     int out_start, out_stride, n_out;   // arithmetic selection (identity: 0, 1, T)
     int* counters;        // one zeroed int per step (dynamic tile tickets)
+    // training with auxiliary storage (step_stream_kernel): I'_k and AI_k = A I'_k of every step are kept for the reverse
+    // sweep in aux[T][2][Mr + 1][H] (Mr = M rounded up to the tile; row Mr of every I' plane is the all-zero row)
+    float* ai_out;        // one launch per step: AI_k plane, or null
+    float* aux;           // persistent rollout: base of the buffer, or null
+    int64_t aux_slot;     // floats per grid point = 2 (Mr + 1) H
+    int ip_zrow;          // row index of the all-zero row of an I' plane (M for the ping-pong buffers)
     alignas(64) CUtensorMap tm_ip_out;   // [M rows][64] fp32 over ip_out, box 32 x 128, SWIZZLE_128B
     alignas(64) CUtensorMap tm_ipb[2];   // the same over ipb[0] / ipb[1] (persistent rollout)
     // step_stream_kernel: the S_k tile arrives by TMA tensor loads (same box / swizzle = the UMMA operand layout)
@@ -1064,7 +1070,7 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
 // with LDG-fed operands (round 1; also the fallback when no tensor map can be encoded), 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 6) : 5; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 7) : 5; }
     return g_step_kernel;
 }
 
@@ -1106,7 +1112,7 @@ static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t str
             const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
 #define GN_SS(O) (fast ? (rf ? launch_step_stream<true, true, O>(b, a, stream) : launch_step_stream<true, false, O>(b, a, stream)) \
                        : (rf ? launch_step_stream<false, true, O>(b, a, stream) : launch_step_stream<false, false, O>(b, a, stream)))
-            return step_kernel_choice() == 6 ? GN_SS(0) : GN_SS(1);
+            return step_kernel_choice() == 6 ? GN_SS(0) : (step_kernel_choice() == 7 ? GN_SS(3) : GN_SS(1));
 #undef GN_SS
         }
         if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
@@ -1163,7 +1169,7 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
-    if (kernel < 0 || kernel > 6 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5 or 6"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 7 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5, 6 or 7"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }
@@ -1246,8 +1252,9 @@ int make_out_sel(int T, const int32_t* out_steps, int32_t n_out, OutSel* o, cons
 }
 
 static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p, int32_t T,
-                                const float* dt_host, const OutSel& sel, float* traj, float* probs, void* workspace,
-                                size_t workspace_bytes, cudaStream_t stream) {
+                                const float* dt_host, const OutSel& sel, float* traj, float* aux, int32_t* aux_filled,
+                                float* probs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (aux_filled) *aux_filled = 0;
     if (workspace_bytes < gnode_rollout_workspace_bytes(b, traj != nullptr)) {
         set_error("gnode_rollout_forward: workspace too small (%zu < %zu)", workspace_bytes,
                   gnode_rollout_workspace_bytes(b, traj != nullptr));
@@ -1277,6 +1284,19 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     }
     auto state = [&](int k) -> float* { return traj ? traj + (size_t)k * 3 * M * H : st[k & 1]; };
     auto out = [&](int k) -> float* { return sel.slot[k] >= 0 ? probs + (size_t)sel.slot[k] * M * 3 : nullptr; };
+    // Auxiliary storage for the reverse sweep (training, stream kernel): the I' plane of EVERY grid point stays in
+    // aux[k][0] (the step writes I'_{k+1} anyway: no extra traffic) and AI_k = A I'_k goes to aux[k][1] (256 B per row
+    // and step more), so that the reverse sweep neither recomputes I' nor repeats the neighbour gather of A I'.
+    const size_t Mr = (M + TILE - 1) / TILE * TILE, Ms = Mr + 1;
+    const size_t aux_slot = 2 * Ms * H;
+    const bool aux_on = aux && traj && T > 1 && use_dual() && step_kernel_choice() >= 5 && !(debug_flags() & 32768) &&
+                        tensor_map_encoder() != nullptr;
+    if (aux_on) {
+        for (int k = 0; k < 2; ++k) ip[k] = nullptr;
+        // the all-zero rows (index Mr of every I' plane)
+        GN_CUDA(cudaMemset2DAsync(aux + Mr * H, aux_slot * sizeof(float), 0, H * sizeof(float), (size_t)T, stream));
+    }
+    auto ipk = [&](int k) -> float* { return aux_on ? aux + (size_t)k * aux_slot : ip[k & 1]; };
 
     StepArgs a{};
     a.bv = gn_view(b);
@@ -1284,7 +1304,8 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     a.beta = beta; a.gamma = gamma;
     a.x = x; a.ldx = ldx;
     a.y_in = nullptr; a.ip_in = nullptr;
-    a.y_out = state(0); a.ip_out = ip[0];
+    a.y_out = state(0); a.ip_out = ipk(0);
+    a.ai_out = nullptr; a.aux = nullptr; a.aux_slot = (int64_t)aux_slot; a.ip_zrow = aux_on ? (int)Mr : (int)M;
     a.probs = out(0); a.dt = 0.f;
     a.out_slot = nullptr; a.out_start = sel.start; a.out_stride = sel.stride; a.n_out = sel.n_out;
     a.dbg = debug_flags();
@@ -1299,7 +1320,9 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     const bool stream_kernel = dual && step_kernel_choice() >= 5;
     a.use_tma = 0;
     CUtensorMap tm_ip[2];
-    const bool have_tma = dual && !(a.dbg & 32768) && encode_rows_map(&tm_ip[0], ip[0], M) && encode_rows_map(&tm_ip[1], ip[1], M);
+    const bool have_tma = dual && !(a.dbg & 32768) &&
+                          (aux_on ? encode_rows_map(&tm_ip[0], aux, (size_t)T * 2 * Ms)        // persistent rollout: one map over the buffer
+                                  : (encode_rows_map(&tm_ip[0], ip[0], M) && encode_rows_map(&tm_ip[1], ip[1], M)));
     a.hid_i = dual ? hid_i : nullptr;
     const bool rfree = dual && !traj && T > 1 && r_state_choice() == 1;
     a.hid_r = rfree ? hid_r : nullptr;
@@ -1314,7 +1337,7 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     const int persistent_mode = persistent_choice();
     const bool persistent_ok = persistent_mode < 0 ? b->n_tiles <= 32 * b->sm_count : persistent_mode != 0;
     int coop = 0;
-    if (dual && persistent_ok && T > 2 && T - 1 <= 1023 && !(a.dbg & 64))
+    if (dual && persistent_ok && T > 2 && T - 1 <= 1023 && !(a.dbg & 64) && (!aux_on || (size_t)T * 2 * Ms < ((size_t)1 << 31)))
         GN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device));
     if (coop) {
         // step sizes / output slots: carried in the kernel parameters when the grid is uniform and the selection an
@@ -1334,6 +1357,7 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
         a.n_steps = T - 1; a.k0 = 0;
         a.traj = traj; a.st[0] = st[0]; a.st[1] = st[1];
         a.ipb[0] = ip[0]; a.ipb[1] = ip[1];
+        a.aux = aux_on ? aux : nullptr;
         a.probs_base = probs; a.counters = counters;
         a.use_tma = have_tma ? 1 : 0;
         if (have_tma) { a.tm_ipb[0] = tm_ip[0]; a.tm_ipb[1] = tm_ip[1]; }
@@ -1342,7 +1366,8 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
                                  : (encode_rows_map(&a.tm_sp[0], st[0], M) && encode_rows_map(&a.tm_sp[1], st[1], M));
             if (ok && (!traj || (size_t)T * 3 * M < ((size_t)1 << 31))) a.use_tma = 2;
         }
-        a.y_in = state(0); a.y_out = state(1); a.ip_in = ip[0]; a.ip_out = ip[1]; a.probs = nullptr; a.dt = dt_host[0];
+        a.y_in = state(0); a.y_out = state(1); a.ip_in = ipk(0); a.ip_out = ipk(1); a.probs = nullptr; a.dt = dt_host[0];
+        if (aux_on && a.use_tma != 2) { set_error("gnode_rollout_forward: tensor maps over the auxiliary buffer could not be encoded"); return GNODE_ERR_CUDA; }
         rc = launch_step<MODE_STEP>(b, a, stream);
         if (rc == GNODE_ERR_CUDA && !persistent_forced()) {
             // e.g. cudaErrorCooperativeLaunchTooLarge under MPS / green-context SM limits: clear it, one launch per step
@@ -1351,13 +1376,17 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
             a.n_steps = 0;
         } else if (rc) return rc;
     }
+    a.aux = nullptr;
     if (!coop)
     for (int k = 0; k + 1 < T; ++k) {
         a.y_in = state(k); a.y_out = state(k + 1);
-        a.ip_in = ip[k & 1]; a.ip_out = ip[(k + 1) & 1];
+        a.ip_in = ipk(k); a.ip_out = ipk(k + 1);
+        a.ai_out = aux_on ? ipk(k) + Ms * H : nullptr;
         a.use_tma = 0;
-        if (have_tma) { a.use_tma = 1; a.tm_ip_out = tm_ip[(k + 1) & 1]; }
-        if (have_tma && stream_kernel && encode_rows_map(&a.tm_s_in, state(k), M)) a.use_tma = 2;
+        if (have_tma && !aux_on) { a.use_tma = 1; a.tm_ip_out = tm_ip[(k + 1) & 1]; }
+        if (have_tma && aux_on && encode_rows_map(&a.tm_ip_out, ipk(k + 1), M)) a.use_tma = 1;     // rows past M clipped
+        if (a.use_tma == 1 && stream_kernel && encode_rows_map(&a.tm_s_in, state(k), M)) a.use_tma = 2;
+        if (aux_on && a.use_tma != 2) { set_error("gnode_rollout_forward: tensor maps over the auxiliary buffer could not be encoded"); return GNODE_ERR_CUDA; }
         // dual kernel: step k decodes its input state k (k = 0 is the encoder's); the others decode their output
         a.probs = dual ? (k > 0 ? out(k) : nullptr) : out(k + 1);
         a.dt = dt_host[k];
@@ -1370,6 +1399,7 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
         decode_kernel<<<grid, 256, 0, stream>>>(state(T - 1), out(T - 1), (int)M, *p, a.hid_r);
         GN_LAUNCH_CHECK();
     }
+    if (aux_filled) *aux_filled = aux_on ? 1 : 0;
     return GNODE_OK;
 }
 
@@ -1418,7 +1448,27 @@ extern "C" int gnode_rollout_forward_sel(gnode_batch_t b, const float* x, int64_
     OutSel sel;
     int rc = make_out_sel(T, out_steps, n_out, &sel, "gnode_rollout_forward_sel");
     if (rc) return rc;
-    return rollout_forward_impl(b, x, ldx, p, T, dt_host, sel, traj, probs, workspace, workspace_bytes, (cudaStream_t)stream_);
+    return rollout_forward_impl(b, x, ldx, p, T, dt_host, sel, traj, nullptr, nullptr, probs, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" size_t gnode_rollout_aux_bytes(gnode_batch_t b, int32_t T) {
+    if (!b || T < 1) return 0;
+    const size_t Mr = ((size_t)b->M + TILE - 1) / TILE * TILE;
+    return (size_t)T * 2 * (Mr + 1) * H * sizeof(float);
+}
+
+extern "C" int gnode_rollout_forward_aux(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                                         int32_t T, const float* dt_host, const int32_t* out_steps, int32_t n_out,
+                                         float* traj, float* aux, int32_t* aux_filled, float* probs, void* workspace,
+                                         size_t workspace_bytes, void* stream_) {
+    if (!b || !x || !p || !probs || !workspace || T < 1 || ldx < 5 || (T > 1 && !dt_host) || (aux && (!traj || !aux_filled))) {
+        set_error("gnode_rollout_forward_aux: bad arguments (T=%d ldx=%lld)", T, (long long)ldx);
+        return GNODE_ERR_ARG;
+    }
+    OutSel sel;
+    int rc = make_out_sel(T, out_steps, n_out, &sel, "gnode_rollout_forward_aux");
+    if (rc) return rc;
+    return rollout_forward_impl(b, x, ldx, p, T, dt_host, sel, traj, aux, aux_filled, probs, workspace, workspace_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int gnode_expand_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr, const float* beta,

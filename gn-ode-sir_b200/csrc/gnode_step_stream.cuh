@@ -110,10 +110,14 @@ struct SStep {
     const CUtensorMap* tm;        // I'_{k+1} store
     const CUtensorMap* tms;       // S_k load
     int srow0;                    // row coordinate of the S plane's first row in tms
+    int iprow0;                   // row coordinate of the I'_{k+1} plane's first row in tm
+    float* ai_out;                // training with auxiliary storage: AI_k = A I'_k of every row (read by the reverse sweep), or null
     float dt;
 };
 
-template <bool FAST, bool PERSIST, bool RF, int OPT>      // OPT bit 0: no block barrier after the I' store (see P5)
+// OPT bit 0: no block barrier after the I' store (see P5); bit 1: no block barrier between the neighbour sums and the
+// row update in tiles whose rows are strided over the warps (every half-warp updates exactly the rows it gathered)
+template <bool FAST, bool PERSIST, bool RF, int OPT>
 __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_constant__ StepArgs a) {
     using C = StreamCfg;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
 #define STP_TM() (PERSIST ? stp->tm : &a.tm_ip_out)
 #define STP_TMS() (PERSIST ? stp->tms : &a.tm_s_in)
 #define STP_SROW0() (PERSIST ? stp->srow0 : 0)
+#define STP_IPROW0() (PERSIST ? stp->iprow0 : 0)
 
     // one thread: draw the next sequence number and resolve its metadata (3 dependent loads of small tables)
     auto fetch_meta = [&](int k) {
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             SStep d;
             d.y_in = a.y_in; d.y_out = a.y_out; d.ip_in = a.ip_in; d.ip_out = a.ip_out;
             d.probs = a.probs; d.counter = a.counter; d.tm = &a.tm_ip_out; d.tms = &a.tm_s_in; d.srow0 = 0; d.dt = a.dt;
+            d.iprow0 = 0; d.ai_out = a.ai_out;
             if (a.n_steps > 0) {                              // persistent rollout: operands of Euler step ks
                 const int ks = a.k0 + step;
                 const size_t plane3 = 3 * (size_t)M * H;
@@ -228,6 +234,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 d.tm = &a.tm_ipb[(ks + 1) & 1];
                 d.tms = a.traj ? &a.tm_sp[0] : &a.tm_sp[ks & 1];
                 d.srow0 = a.traj ? ks * 3 * M : 0;
+                if (a.aux) {                                  // I'_k / AI_k of every step are kept for the reverse sweep
+                    d.ip_in = a.aux + (size_t)ks * a.aux_slot; d.ip_out = a.aux + (size_t)(ks + 1) * a.aux_slot;
+                    d.ai_out = a.aux + (size_t)ks * a.aux_slot + a.aux_slot / 2;
+                    d.tm = &a.tm_ipb[0];                      // one map over the whole buffer, rows = T * 2 * (Mr + 1)
+                    d.iprow0 = (int)((size_t)(ks + 1) * (a.aux_slot / H));
+                }
             }
             *stp = d;
         }
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         // row pairs of the neighbour gather: strided over the warps when the tile's CSR slice fits the staged window,
         // shared-memory tickets for hub tiles so that a long row does not leave the other warps idle
         const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
-        const int zrow = M - i_row0;                         // the all-zero row that follows the I' rows
+        const int zrow = a.ip_zrow - i_row0;                 // the all-zero row that follows the I' rows
         const bool static_rows = m.ecnt <= C::CAP;
         int sj = 0;
         auto draw_pair = [&]() -> int {
@@ -388,9 +400,11 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
         };
         // what the gathering half-warp does with the finished neighbour sum of row rr: AI * S' replaces S' in place
+        float* const ai_out = STP(ai_out);
         auto finish_row = [&](int rr, bool ok, float4 acc) {
             const int o = C::sw(rr, l);
             const float4 sp = lds4(Ls, o);
+            if (ai_out != nullptr && ok) stg4_hint(ai_out + (size_t)(tile0 + rr) * H + 4 * l, acc, pol_stream);
             if (ok) sts4(Ls, o, make_float4(__fmul_rn(acc.x, sp.x), __fmul_rn(acc.y, sp.y), __fmul_rn(acc.z, sp.z), __fmul_rn(acc.w, sp.w)));
         };
 
@@ -483,7 +497,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
         }
         {
-            HSYNC();                                                            // S2b: every AI * S' row is parked
+            // S2b: every AI * S' row is parked. With strided rows (and in multi-instance tiles) half-warp hw gathers the
+            // rows hw + 32 it and updates the same rows, each lane its own 16 bytes: no other warp's data is read below,
+            // so fast warps start their update while slow ones still wait for neighbour rows (tile-uniform condition)
+            if (!(OPT & 2) || (single && !static_rows) || relay) HSYNC();
             // ---- P3b: SIR update (own I_k / I'_k rows one pass ahead in registers; S_k from the raw operand tile; the
             //      lane's 4 x 4 linear3 weights stay in registers for the four passes)
             const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),
@@ -557,8 +574,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         HSYNC();                                                                // S4 (the next tile's metadata is published)
         // ---- P5: I'_{k+1} tile -> HBM by two TMA tensor stores (rows past M are clipped by the tensor bounds)
         if (t == 0) {
-            tma_store_2d(STP_TM(), Ls, 0, tile0, pol_stream);
-            tma_store_2d(STP_TM(), Ls + C::KBLK, 32, tile0, pol_stream);
+            tma_store_2d(STP_TM(), Ls, 0, STP_IPROW0() + tile0, pol_stream);
+            tma_store_2d(STP_TM(), Ls + C::KBLK, 32, STP_IPROW0() + tile0, pol_stream);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             // OPT bit 0: no block barrier here. The staged tile may be overwritten once the bulk group has read it; the next
@@ -579,6 +596,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
 #undef STP_TM
 #undef STP_TMS
 #undef STP_SROW0
+#undef STP_IPROW0
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(*tslot, C::TMEM_COLS);

@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory, the stream and autograd's graph
 all arithmetic of the path runs in libgnode_b200.so.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -11,6 +12,9 @@ import torch
 from . import _lib
 
 H = _lib.GNODE_H
+# training keeps I'_k and A I'_k of every Euler step beside the trajectory (5 instead of 3 state planes per grid point)
+# so that the reverse sweep gathers once per step; False = trajectory only (less memory, two gathers per reverse step)
+AUX_STORAGE = os.environ.get("GNODE_AUX_STORAGE", "1") != "0"
 PARAM_ORDER = tuple(k for k, _ in _lib.GRAD_LAYOUT)
 
 
@@ -109,13 +113,24 @@ class _Rollout(torch.autograd.Function):
             ws_bytes = int(L.gnode_rollout_workspace_bytes(batch.handle, 1 if need_grad else 0))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             pstruct = _params_struct(ps)
-            _lib.check(L.gnode_rollout_forward_sel(batch.handle, _ptr(x), x.stride(0), ctypes.byref(pstruct), T,
+            # training: I'_k and A I'_k of every step are kept for the reverse sweep (one neighbour gather per reverse
+            # step instead of two, no recomputed I'); AUX_STORAGE = False restores the trajectory-only sweep
+            aux, filled = None, ctypes.c_int32(0)
+            if need_grad and AUX_STORAGE and T > 1:
+                try:
+                    aux = torch.empty(int(L.gnode_rollout_aux_bytes(batch.handle, T)) // 4, dtype=torch.float32, device=x.device)
+                except torch.cuda.OutOfMemoryError:          # 2/3 of the trajectory's size on top of it: optional
+                    aux = None
+            _lib.check(L.gnode_rollout_forward_aux(batch.handle, _ptr(x), x.stride(0), ctypes.byref(pstruct), T,
                                                    dt.ctypes.data_as(_lib.c_float_p), steps_p, n_out,
-                                                   _ptr(traj) if need_grad else None, _ptr(probs), _ptr(ws), ws_bytes,
-                                                   _stream(x.device)), "gnode_rollout_forward_sel")
+                                                   _ptr(traj) if need_grad else None,
+                                                   _ptr(aux) if aux is not None else None, ctypes.byref(filled),
+                                                   _ptr(probs), _ptr(ws), ws_bytes,
+                                                   _stream(x.device)), "gnode_rollout_forward_aux")
         if need_grad:
             ctx.save_for_backward(x, traj, *ps)
             ctx.batch, ctx.dt, ctx.grad_mode, ctx.steps = batch, dt, grad_mode, steps
+            ctx.aux = aux if filled.value == 1 else None
         return probs
 
     @staticmethod
@@ -134,11 +149,12 @@ class _Rollout(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             pstruct = _params_struct(ps)
             mode = {"adjoint": _lib.GRAD_ADJOINT, "discrete": _lib.GRAD_DISCRETE}[ctx.grad_mode]
-            _lib.check(L.gnode_rollout_backward_sel(batch.handle, _ptr(x), x.stride(0), ctypes.byref(pstruct), T,
-                                                    dt.ctypes.data_as(_lib.c_float_p), _ptr(traj), _ptr(grad_probs),
+            _lib.check(L.gnode_rollout_backward_aux(batch.handle, _ptr(x), x.stride(0), ctypes.byref(pstruct), T,
+                                                    dt.ctypes.data_as(_lib.c_float_p), _ptr(traj),
+                                                    _ptr(ctx.aux) if ctx.aux is not None else None, _ptr(grad_probs),
                                                     steps_p, len(steps) if steps is not None else 0, mode,
                                                     _ptr(grads), _ptr(ws), ws_bytes, _stream(x.device)),
-                       "gnode_rollout_backward_sel")
+                       "gnode_rollout_backward_aux")
         out, off = [], 0
         for i, (k, shape) in enumerate(_lib.GRAD_LAYOUT):
             n = int(np.prod(shape))

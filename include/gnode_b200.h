@@ -203,6 +203,25 @@ int gnode_rollout_backward_sel(gnode_batch_t b, const float* x, int64_t ldx, con
                                const int32_t* out_steps, int32_t n_out, int32_t grad_mode, float* grads_out,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training with auxiliary storage (round 2) ---------------------------------
+ * The reverse sweep of torchdiffeq's adjoint re-evaluates f at every stored state (OdeintAdjointMethod.backward), i.e.
+ * it recomputes I' = sigmoid(linear(I_j)) and repeats the neighbour gather A I' of ode_nn_ngraph_sim.py:62-73. The
+ * forward already holds both: it writes I'_{k+1} for the next step's gather and sums AI_k row by row. With an `aux`
+ * buffer of gnode_rollout_aux_bytes(b, T) bytes ([T][2][Mr + 1][H] fp32, Mr = M rounded up to 128) the forward keeps
+ * I'_k of every grid point (no extra traffic) and AI_k (256 B per row and step more), and the reverse sweep runs three
+ * launches with ONE neighbour gather per step instead of four launches with two.
+ *   aux_filled (HOST int32, out): 1 if the buffer was filled (default step kernel with tensor maps available), else 0
+ *   -- pass aux to gnode_rollout_backward_aux only when it is 1, NULL otherwise. aux == NULL: exactly the _sel calls. */
+size_t gnode_rollout_aux_bytes(gnode_batch_t b, int32_t T);
+int gnode_rollout_forward_aux(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                              int32_t T, const float* dt_host, const int32_t* out_steps, int32_t n_out,
+                              float* traj, float* aux, int32_t* aux_filled, float* probs, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int gnode_rollout_backward_aux(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p,
+                               int32_t T, const float* dt_host, const float* traj, const float* aux,
+                               const float* grad_probs, const int32_t* out_steps, int32_t n_out, int32_t grad_mode,
+                               float* grads_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- N1: L1 loss on the sub-sampled prediction and its cotangent, fused -------
  * Replaces, per mini-batch, get_sir_t_nodes_torch x3 (60 row copies device -> CPU tensor, ode_nn.py:257-259), the
  * cat / transpose / .to(device) and nn.L1Loss on [:,1:,:] (ode_nn_ngraph_sim.py:230-234, ode_nn_ngraphs.py:216-220),

@@ -145,6 +145,55 @@ def forward(x, params, coo, t, return_traj=False, rebuild_index=None):
     return (probs, traj) if return_traj else probs
 
 
+def neighbour_sum_chunked(Ip, rowptr, colidx, rows_per_chunk=1 << 17):
+    """neighbour_sum for graphs whose [nnz, H] gather + repeated int64 index (ode_nn_ngraph_sim.py:73) does not fit
+    host memory (BA N=2M: 30 GB): the same gather + scatter_add_ over consecutive row ranges of the row-major COO.
+    scatter_add_ on CPU accumulates every output row in index order, so cutting the COO between rows leaves each row's
+    sum bitwise unchanged (tests/test_oracle_golden.py::test_streaming_forward_is_bitwise_forward)."""
+    H = Ip.size(1)
+    M = Ip.size(0)
+    out = torch.zeros(Ip.size(), dtype=Ip.dtype)
+    rp = torch.as_tensor(rowptr, dtype=torch.int64)
+    ci = torch.as_tensor(colidx, dtype=torch.int64)
+    for r0 in range(0, M, rows_per_chunk):
+        r1 = min(M, r0 + rows_per_chunk)
+        e0, e1 = int(rp[r0]), int(rp[r1])
+        if e1 == e0:
+            continue
+        rows = torch.repeat_interleave(torch.arange(r0, r1), rp[r0 + 1:r1 + 1] - rp[r0:r1]) - r0
+        out[r0:r1].scatter_add_(0, rows.unsqueeze(1).repeat(1, H), Ip[ci[e0:e1]])
+    return out
+
+
+def forward_streaming(x, params, A, t, out_steps=None):
+    """forward() for ONE instance of a graph too large for the [T,3,M,H] trajectory and the [nnz,H] gather: the same
+    operations in the same order (encode, rhs with the chunked neighbour sum, Euler update, decode), keeping only the
+    current state; probabilities of the grid points in out_steps (default: all). A: scipy CSR with sorted indices."""
+    A = scipy.sparse.csr_matrix(A)
+    A.sort_indices()
+    S, I, R, beta, gamma = encode(x, _p(params, "linearS1.weight"), _p(params, "linearS1.bias"))
+    W, b = _p(params, "odefunc.linear.weight"), _p(params, "odefunc.linear.bias")
+    dec = lambda S_, I_, R_: decode(S_, I_, R_, _p(params, "linear3.weight"), _p(params, "linear3.bias"),
+                                    _p(params, "linearS2.weight"), _p(params, "linearS2.bias"))
+    keep = set(range(len(t))) if out_steps is None else set(int(k) for k in out_steps)
+    out = []
+    M = S.size(0)
+    for k in range(len(t)):
+        if k in keep:
+            out.append(dec(S, I, R))
+        if k + 1 == len(t):
+            break
+        dt = t[k + 1] - t[k]
+        Z = torch.sigmoid(F.linear(torch.cat((S, I, R)), W, b))
+        Sp, Ip = Z[:M], Z[M:2 * M]
+        AI = neighbour_sum_chunked(Ip, A.indptr, A.indices)
+        dS = -beta.unsqueeze(-1) * torch.multiply(AI, Sp)
+        dI = -dS - gamma.unsqueeze(-1) * Ip
+        dR = gamma.unsqueeze(-1) * Ip
+        S, I, R = S + dt * dS, I + dt * dI, R + dt * dR
+    return torch.stack(out)
+
+
 # --------------------------------------------------------------------------
 # gradients
 # --------------------------------------------------------------------------

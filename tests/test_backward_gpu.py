@@ -175,3 +175,67 @@ def test_training_step_reduces_loss(gn):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0]
+
+
+@pytest.fixture
+def no_aux(gn):
+    """Trajectory-only reverse sweep (four launches, two neighbour gathers per step): the path that also runs when the
+    forward could not fill the auxiliary I' / A I' storage."""
+    prev = gn.rollout.AUX_STORAGE
+    gn.rollout.AUX_STORAGE = False
+    yield
+    gn.rollout.AUX_STORAGE = prev
+
+
+@pytest.mark.parametrize("mode", ["adjoint", "discrete"])
+@pytest.mark.parametrize("name", ["sim_karate_b8", "ng_mixed_b5"])
+def test_gradients_without_auxiliary_storage(gn, no_aux, name, mode):
+    """The goldens' gradients through the trajectory-only sweep (the default tests above run with the forward's
+    auxiliary storage)."""
+    g = Golden(name)
+    blk, _ = cuda_grads(gn, g, mode)
+    got = {k: p.grad.detach().cpu() for k, p in blk.named_parameters() if p.grad is not None}
+    for k in orc.GRAD_KEYS:
+        ref32 = g.grads[("g32", mode)][k]
+        scale = max(g.grads[("g64", mode)][k].abs().max().item(), 1.0)
+        assert (got[k] - ref32).abs().max().item() / scale < 2e-4, k
+
+
+@pytest.mark.parametrize("persistent", [0, 1], ids=["launch-per-step", "cooperative"])
+@pytest.mark.parametrize("mode", ["adjoint", "discrete"])
+def test_auxiliary_storage_sweep_equals_trajectory_sweep(gn, mode, persistent):
+    """Same batch, same cotangent: the sweep that reads I'_j and A I'_j kept by the forward (three launches, one gather
+    per step; dense cotangent in adjoint mode: grid point T-1 has no stored A I' and takes the four-launch step) against
+    the trajectory-only sweep. The two differ only in the evaluation order of a few products: 2e-5 of the largest entry.
+    M = 5 * 620 + ragged tail: partial last tile, rows past M in the padded I' planes."""
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
+    g = Golden("sim_fbfood_b2")
+    A, N, B = g.adjs[0], g.adjs[0].shape[0], 5
+    params = {k: v.to(DEV).requires_grad_(k in orc.GRAD_KEYS) for k, v in orc.default_params(64, seed=5).items()}
+    order = gn.rollout.PARAM_ORDER
+    x = torch.cat([orc.synthetic_trial(N, 64, 60 + b) for b in range(B)]).to(DEV)
+    t = orc.time_grid(8, 0.5)
+    dt = gn.rollout.dt_array(t)
+    batch = gn.DeviceBatch([gn.DeviceGraph(A)] * B)
+    w = torch.randn(len(t), B * N, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    prev_p = L.gnode_get_persistent()
+    grads, probs = {}, {}
+    try:
+        _lib.check(L.gnode_set_persistent(persistent), "set_persistent")
+        for aux in (True, False):
+            gn.rollout.AUX_STORAGE = aux
+            for p in params.values():
+                p.grad = None
+            out = gn.rollout.rollout(x, batch, dt, [params[k] for k in order], grad_mode=mode)
+            (out * w).sum().backward()
+            grads[aux] = {k: params[k].grad.detach().clone() for k in order}
+            probs[aux] = out.detach().clone()
+    finally:
+        gn.rollout.AUX_STORAGE = True
+        L.gnode_set_persistent(prev_p)
+    assert torch.equal(probs[True], probs[False])            # the forward's arithmetic does not depend on the storage
+    for k in order:
+        scale = max(grads[False][k].abs().max().item(), 1e-3)
+        err = (grads[True][k] - grads[False][k]).abs().max().item() / scale
+        assert err < 2e-5, (k, err)

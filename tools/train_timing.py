@@ -5,7 +5,7 @@ import numpy as np, torch
 import gn_ode_sir_b200 as gn
 from gn_ode_sir_b200 import synth
 dev = torch.device("cuda:0")
-for name, n, m, B in (("karate-size", 34, 2, 1), ("fb-social-size", 1893, 7, 8), ("fb-social-size", 1893, 7, 64), ("epinions-size", 75879, 5, 4)):
+for name, n, m, B in (("karate-size", 34, 2, 1), ("fb-social-size", 1893, 7, 8), ("fb-social-size", 1893, 7, 64), ("epinions-size", 75879, 5, 4), ("epinions-size", 75879, 5, 8)):
     A = synth.barabasi_albert_csr(n, m, 0); N = A.shape[0]
     torch.manual_seed(0)
     of = gn.ode_sim.ODEfunc(A, 0.2, 0.1, 64, dev); blk = gn.ode_sim.ODEBlock(20, 0.5, N, [0, 1], 64, of, dev).to(dev)
