@@ -42,6 +42,8 @@ SIGNATURES = {
     "gnode_get_persistent": (c_int, []),
     "gnode_set_hub_relay": (c_int, [c_int]),
     "gnode_get_hub_relay": (c_int, []),
+    "gnode_set_bwd_kernel": (c_int, [c_int]),
+    "gnode_get_bwd_kernel": (c_int, []),
     "gnode_debug_phase_cycles": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "gnode_graph_create": (c_int, [c_int32, c_int64, c_int32_p, c_int32_p, ctypes.POINTER(c_void_p)]),
     "gnode_graph_destroy": (c_int, [c_void_p]),

@@ -753,10 +753,27 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_slo
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// 2 (default) = bwd_vjp2_kernel (two 256-thread CTAs per SM, parts in sequence), 1 = bwd_vjp_kernel; env GNODE_BWD_VJP
+// 2 (default) = bwd_vjp2_kernel (two 256-thread CTAs per SM, parts in sequence), 1 = bwd_vjp_kernel; env GNODE_BWD_VJP.
+// (The weight gradient vW = gz^T X on tcgen05 was probed and not built: kind::tf32 takes MN-major operands only in the
+// SWIZZLE_128B_BASE32B layout -- 32-byte swizzle granules; with the plain SWIZZLE_128B descriptor the instruction
+// completes and leaves zeros, tools/umma_mn_probe.cu, profiles/r2k_umma_mn_probe.log -- while v = gz W needs the same gz
+// tile K-major in plain SWIZZLE_128B: two copies of gz (hi and lo each) beside the split state tile = six operand
+// tiles, 192 KB + the W^T operand, with one CTA per SM left to hide the loads.)
+static int g_vjp_kernel = 0;
 static int vjp_kernel_choice() {
-    static const int c = getenv("GNODE_BWD_VJP") ? atoi(getenv("GNODE_BWD_VJP")) : 2;
-    return c == 1 ? 1 : 2;
+    if (g_vjp_kernel == 0) {
+        const int c = getenv("GNODE_BWD_VJP") ? atoi(getenv("GNODE_BWD_VJP")) : 2;
+        g_vjp_kernel = (c >= 1 && c <= 2) ? c : 2;
+    }
+    return g_vjp_kernel;
+}
+static int launch_vjp(const BwdArgs& a, int grid, cudaStream_t stream) {
+    switch (vjp_kernel_choice()) {
+        case 1: bwd_vjp_kernel<<<grid, NTHREADS, K3_SM_TOTAL, stream>>>(a); break;
+        default: bwd_vjp2_kernel<<<grid, K3B_THREADS, K3B_SM_TOTAL, stream>>>(a); break;
+    }
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
 }
 
 struct BwdPlan {
@@ -787,6 +804,13 @@ static BwdPlan plan_backward(const gnode_batch* b) {
 }  // namespace gnode
 
 using namespace gnode;
+
+extern "C" int gnode_set_bwd_kernel(int kernel) {
+    if (kernel < 1 || kernel > 2) { set_error("gnode_set_bwd_kernel: kernel must be 1 or 2"); return GNODE_ERR_ARG; }
+    g_vjp_kernel = kernel;
+    return GNODE_OK;
+}
+extern "C" int gnode_get_bwd_kernel(void) { return vjp_kernel_choice(); }
 
 extern "C" size_t gnode_backward_workspace_bytes(gnode_batch_t b) {
     if (!b) return 0;
@@ -921,10 +945,7 @@ extern "C" int gnode_rollout_backward_aux(gnode_batch_t b, const float* x, int64
             bwd_gz_kernel<true><<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
             GN_LAUNCH_CHECK();
             a.part = plin;
-            if (vjp_kernel_choice() == 2) bwd_vjp2_kernel<<<pl.grid_tile3, K3B_THREADS, K3B_SM_TOTAL, stream>>>(a);
-            else bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
-            GN_LAUNCH_CHECK();
-            return GNODE_OK;
+            return launch_vjp(a, pl.grid_tile3, stream);
         }
         a.y = state(j); a.gP = with_decoder ? gp(j) : nullptr; a.dt = dt; a.only_dec = 0;
         a.part = nullptr;
@@ -937,10 +958,7 @@ extern "C" int gnode_rollout_backward_aux(gnode_batch_t b, const float* x, int64
         bwd_gz_kernel<false><<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
         a.part = plin;
-        if (vjp_kernel_choice() == 2) bwd_vjp2_kernel<<<pl.grid_tile3, K3B_THREADS, K3B_SM_TOTAL, stream>>>(a);
-        else bwd_vjp_kernel<<<pl.grid_tile3, NTHREADS, K3_SM_TOTAL, stream>>>(a);
-        GN_LAUNCH_CHECK();
-        return GNODE_OK;
+        return launch_vjp(a, pl.grid_tile3, stream);
     };
     int jmax = T - 1;                             // last grid point with a cotangent: the adjoint is zero beyond it
     while (jmax > 0 && sel.slot[jmax] < 0) --jmax;

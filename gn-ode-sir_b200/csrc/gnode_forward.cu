@@ -1070,7 +1070,7 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
 // with LDG-fed operands (round 1; also the fallback when no tensor map can be encoded), 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 7) : 5; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 6) : 5; }
     return g_step_kernel;
 }
 
@@ -1112,7 +1112,7 @@ static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t str
             const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
 #define GN_SS(O) (fast ? (rf ? launch_step_stream<true, true, O>(b, a, stream) : launch_step_stream<true, false, O>(b, a, stream)) \
                        : (rf ? launch_step_stream<false, true, O>(b, a, stream) : launch_step_stream<false, false, O>(b, a, stream)))
-            return step_kernel_choice() == 6 ? GN_SS(0) : (step_kernel_choice() == 7 ? GN_SS(3) : GN_SS(1));
+            return step_kernel_choice() == 6 ? GN_SS(0) : GN_SS(1);
 #undef GN_SS
         }
         if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
@@ -1169,7 +1169,7 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
-    if (kernel < 0 || kernel > 7 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5, 6 or 7"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 6 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5 or 6"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }

@@ -115,9 +115,7 @@ struct SStep {
     float dt;
 };
 
-// OPT bit 0: no block barrier after the I' store (see P5); bit 1: no block barrier between the neighbour sums and the
-// row update in tiles whose rows are strided over the warps (every half-warp updates exactly the rows it gathered)
-template <bool FAST, bool PERSIST, bool RF, int OPT>
+template <bool FAST, bool PERSIST, bool RF, int OPT>      // OPT bit 0: no block barrier after the I' store (see P5)
 __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_constant__ StepArgs a) {
     using C = StreamCfg;
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
@@ -497,10 +495,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
         }
         {
-            // S2b: every AI * S' row is parked. With strided rows (and in multi-instance tiles) half-warp hw gathers the
-            // rows hw + 32 it and updates the same rows, each lane its own 16 bytes: no other warp's data is read below,
-            // so fast warps start their update while slow ones still wait for neighbour rows (tile-uniform condition)
-            if (!(OPT & 2) || (single && !static_rows) || relay) HSYNC();
+            // S2b: every AI * S' row is parked. (With strided rows every half-warp updates exactly the rows it gathered and
+            // the barrier could be skipped: measured, 1.668e9 vs 1.677e9 node-steps/s with it, profiles/r2j_ab_no_s2b_barrier.log
+            // -- warps that run ahead only add update-phase loads to a memory system the gather already saturates.)
+            HSYNC();
             // ---- P3b: SIR update (own I_k / I'_k rows one pass ahead in registers; S_k from the raw operand tile; the
             //      lane's 4 x 4 linear3 weights stay in registers for the four passes)
             const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),

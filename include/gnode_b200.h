@@ -103,6 +103,12 @@ int gnode_get_persistent(void);
  * half-warp. Both give BITWISE the same sums; the switch exists for that check and for A/B measurements. */
 int gnode_set_hub_relay(int on);
 int gnode_get_hub_relay(void);
+/* Tile kernel of the reverse sweep (state VJP v = gz W on tcgen05 and weight gradient vW = gz^T X by register-blocked
+ * FFMA per 128-row tile): 2 (default) = two 256-thread CTAs per SM, the two halves of a tile in sequence, next unit
+ * prefetched behind the adjoint's read-modify-write; 1 = the round-1 one-CTA kernel. Env GNODE_BWD_VJP sets the initial
+ * value. Process-wide. Gradients of the two agree to fp32 summation-order noise. */
+int gnode_set_bwd_kernel(int kernel);
+int gnode_get_bwd_kernel(void);
 /* debug: per-phase SM-cycle sums of the step kernel collected while env GNODE_DBG has bit 7 set; resets them */
 int gnode_debug_phase_cycles(long long* out8);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */

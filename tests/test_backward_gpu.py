@@ -239,3 +239,31 @@ def test_auxiliary_storage_sweep_equals_trajectory_sweep(gn, mode, persistent):
         scale = max(grads[False][k].abs().max().item(), 1e-3)
         err = (grads[True][k] - grads[False][k]).abs().max().item() / scale
         assert err < 2e-5, (k, err)
+
+
+@pytest.mark.parametrize("mode", ["adjoint", "discrete"])
+@pytest.mark.parametrize("name", ["sim_karate_b8", "ng_mixed_b5", "sim_fbfood_b2"])
+def test_tile_kernels_of_the_reverse_sweep_agree(gn, name, mode):
+    """The two tile kernels of the reverse sweep (2 = two CTAs per SM with the next unit prefetched, 1 = round 1's
+    one-CTA kernel): every gradient within 2e-5 of the largest entry, and kernel 1 against the reference's own gradients
+    at the suite's tolerance (kernel 2 is the default every other test runs)."""
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
+    g = Golden(name)
+    prev = L.gnode_get_bwd_kernel()
+    got = {}
+    try:
+        for k in (2, 1):
+            _lib.check(L.gnode_set_bwd_kernel(k), "gnode_set_bwd_kernel")
+            blk, _ = cuda_grads(gn, g, mode)
+            got[k] = {n: p.grad.detach().cpu() for n, p in blk.named_parameters() if p.grad is not None}
+    finally:
+        L.gnode_set_bwd_kernel(prev)
+    for k in orc.GRAD_KEYS:
+        scale = max(got[2][k].abs().max().item(), 1e-3)
+        for other in (1,):
+            err = (got[other][k] - got[2][k]).abs().max().item() / scale
+            assert err < 2e-5, (other, k, err)
+        ref32 = g.grads[("g32", mode)][k]
+        rscale = max(g.grads[("g64", mode)][k].abs().max().item(), 1.0)
+        assert (got[1][k] - ref32).abs().max().item() / rscale < 2e-4, k
