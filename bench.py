@@ -54,10 +54,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch(rows):
+def traffic_file(workload):
+    return "profiles/step_kernel_traffic.json" if workload == "epinions" else "profiles/step_kernel_traffic_%s.json" % workload
+
+
+def ncu_traffic_per_launch(rows, workload="epinions"):
     """DRAM bytes per step-kernel launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed
-    `ncu --set full` capture (profiles/step_kernel_traffic.json holds bytes per row of that capture)."""
-    p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    `ncu --set full` capture of this workload (profiles/step_kernel_traffic*.json hold bytes per row of the capture)."""
+    p = os.path.join(ROOT, traffic_file(workload))
     if os.path.exists(p):
         with open(p) as fh:
             return float(json.load(fh)["dram_bytes_per_row"]) * rows
@@ -430,14 +434,14 @@ def main():
     rows_per_launch = local_rows / n_chunks
     peak, peak_src = measured_peak()
     achieved = rows_per_launch * ALGO_BYTES_PER_NODE_STEP / (step_ms * 1e-3) / 1e9
-    traffic = ncu_traffic_per_launch(rows_per_launch)
+    traffic = ncu_traffic_per_launch(rows_per_launch, args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": "gnode::step_stream_kernel (fused Euler step: TMA-fed S tile, tcgen05 transform, CSR gather, SIR update; "
                           "the chunk's expansion, encoder and final decode launches are charged to it)",
                 "launch_ms": step_ms, "rows_per_launch": rows_per_launch,
                 "algorithmic_bytes_per_node_step": ALGO_BYTES_PER_NODE_STEP, "peak_source": peak_src,
-                "traffic_source": "profiles/step_kernel_traffic.json (ncu --set full dram bytes per row of the committed capture) x rows",
+                "traffic_source": "%s (ncu --set full dram bytes per row of the committed capture) x rows" % traffic_file(args.workload),
                 "r_state": R_STATE_NOTE[int(L.gnode_get_r_state())]}
     del out_full, dev_sets
 
