@@ -317,6 +317,71 @@ __global__ void __launch_bounds__(ROW_THREADS, 3) bwd_row_kernel(const BwdArgs a
     }
 }
 
+// ---------------------------------------------------------------- decoder backward alone
+// a += D(y_j, gP_j) for every row (grid points with a cotangent, auxiliary-storage sweep and discrete mode): the
+// streaming part of bwd_row_kernel without its gather. The six row operands (y and a planes) are requested together, so
+// an iteration pays one memory round trip instead of two (bwd_row_kernel reads the adjoint after the decoder's shuffles).
+__global__ void __launch_bounds__(ROW_THREADS, 2) bwd_dec_kernel(const BwdArgs a) {
+    __shared__ float W3s[4 * H];
+    __shared__ float small[12];
+    __shared__ float red[ROW_THREADS / 16][16][17];   // [half-warp][lane][16 w3 values (+pad)]
+    __shared__ float red0[ROW_THREADS / 16][9];       // lane-0 values: b3[4], w2[4], b2
+    const int tid = threadIdx.x, l = tid & 15, hw = tid >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    for (int i = tid; i < 4 * H; i += ROW_THREADS) W3s[i] = a.p.l3_w[i];
+    if (tid < 4) { small[tid] = a.p.l3_b[tid]; small[4 + tid] = a.p.s2_w[tid]; }
+    if (tid == 0) small[8] = a.p.s2_b[0];
+    __syncthreads();
+    DecAcc acc;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc.w3[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc.b3[i] = 0.f; acc.w2[i] = 0.f; }
+    acc.b2 = 0.f;
+    const int hw_per_grid = gridDim.x * (ROW_THREADS / 16);
+    const int64_t n_iter = (M + hw_per_grid - 1) / hw_per_grid;      // warp-uniform trip count (full-mask shuffles inside)
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t g = it * hw_per_grid + (int64_t)blockIdx.x * (ROW_THREADS / 16) + hw;
+        const bool valid = g < M;
+        const size_t off = (size_t)(valid ? g : 0) * H + 4 * l;
+        float4 c[3], av[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            c[k] = valid ? ldg4_stream(a.y + k * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            av[k] = valid ? ldg4(a.a + k * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        decoder_backward_row(c, valid ? a.gP + (size_t)g * 3 : nullptr, W3s, small, l, valid, d, acc);
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                av[k].x += d[k].x; av[k].y += d[k].y; av[k].z += d[k].z; av[k].w += d[k].w;
+                stg4(a.a + k * plane + off, av[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[hw][l][i] = acc.w3[i];
+    if (l == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { red0[hw][i] = acc.b3[i]; red0[hw][4 + i] = acc.w2[i]; }
+        red0[hw][8] = acc.b2;
+    }
+    __syncthreads();
+    float* slot = a.part + (size_t)blockIdx.x * DEC_COUNT;
+    if (tid < 4 * H) {
+        const int m = tid / H, h = tid % H;
+        float s = 0.f;
+        for (int w = 0; w < ROW_THREADS / 16; ++w) s += red[w][h >> 2][4 * m + (h & 3)];
+        slot[tid] += s;
+    }
+    if (tid < 9) {
+        float s = 0.f;
+        for (int w = 0; w < ROW_THREADS / 16; ++w) s += red0[w][tid];
+        slot[4 * H + tid] += s;
+    }
+}
+
 // ---------------------------------------------------------------- K3a
 // Row kernel (half-warp per row, grid-stride): A^T gAI, then the cotangents wrt the pre-activations
 //   gzI = (A^T gAI + gamma (aR - aI)) I'(1-I')      gzS = beta (aI - aS) AI S'(1-S')
@@ -927,7 +992,7 @@ extern "C" int gnode_rollout_backward_aux(gnode_batch_t b, const float* x, int64
     auto dec_only = [&](int j) -> int {
         if (!gp(j)) return GNODE_OK;
         a.y = state(j); a.gP = gp(j); a.part = pdec; a.only_dec = 1; a.dt = 0.f;
-        bwd_row_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
+        bwd_dec_kernel<<<pl.grid_row, ROW_THREADS, 0, stream>>>(a);
         GN_LAUNCH_CHECK();
         return GNODE_OK;
     };

@@ -1147,7 +1147,7 @@ static EncodeTiledFn tensor_map_encoder() {
 }
 
 // [rows][64] fp32 row-major, box = 32 floats (one 128-byte swizzle span) x 128 rows
-static bool encode_rows_map(CUtensorMap* tm, float* base, size_t rows) {
+bool encode_rows_map(CUtensorMap* tm, float* base, size_t rows) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc || rows == 0) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)rows};
