@@ -91,6 +91,7 @@ struct gnode_batch {
     int2* d_sched = nullptr;         // [n_tiles] by sequence number: {tile, first row of the look-ahead I' prefetch or -1}
     int4* d_tile_meta = nullptr;     // [n_tiles] {first CSR entry, entry count, owning instance, bit 0: inside one instance, bit 1: hub relay}
     int4* d_sub_meta = nullptr;      // [2 n_tiles] the same for the two 64-row halves of every tile
+    uint8_t* d_tile_perm = nullptr;  // [n_tiles][128] gather slot -> tile row: rows of similar degree share a warp (row pairs)
     int device = 0;
     int sm_count = 0;
     // captured reverse sweeps of launch-bound batches (gnode_rollout_backward): key of all arguments -> cudaGraphExec_t
@@ -107,6 +108,7 @@ struct GnBatchView {
     const int2* sched;
     const int4* tile_meta;
     const int4* sub_meta;
+    const uint8_t* tile_perm;
     int32_t n_inst;
     int32_t n_tiles;
     int32_t M;
@@ -120,6 +122,7 @@ inline GnBatchView gn_view(const gnode_batch* b) {
     v.sched = b->d_sched;
     v.tile_meta = b->d_tile_meta;
     v.sub_meta = b->d_sub_meta;
+    v.tile_perm = b->d_tile_perm;
     v.n_inst = b->n_inst;
     v.n_tiles = b->n_tiles;
     v.M = (int32_t)b->M;

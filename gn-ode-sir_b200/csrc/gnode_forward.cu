@@ -459,7 +459,8 @@ struct PipeCfg {
     static constexpr int P_CI = P_HR + TR * 16;            // colidx slice (instance-local ids) + 64 B over-read pad
     static constexpr int P_BYTES = ((P_CI + CAP * 4 + 64 + 1023) / 1024) * 1024;
     static constexpr int TOTAL = D_SHARED + NP * P_BYTES + 1024;
-    static constexpr int TMEM_COLS = 128 * NP;             // one [TR x 80] accumulator per pipeline, 128 columns apart
+    static constexpr int TMEM_COLS = 512;                  // one [TR x 160] accumulator per pipeline, 256 columns apart
+    static_assert(NP == 2, "the N = 160 accumulators of more than two pipelines do not fit the 512 TMEM columns");
     static_assert(TOTAL + 1024 <= 200704, "stay inside the 196 KB shared-memory carve-out (60 KB of L1 left)");
     static_assert(PT / 4 >= TR, "beta / gamma staging needs a quarter of the pipeline's threads per array");
     static_assert((TR + 2 + TR / 32) * 4 <= TR * 4 + 32, "hub mask lives in the pad behind the rowptr slice");
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         *meta = m;
     };
 
-    umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
+    umma::prepare_weights160(a.p.lin_w, a.p.l3_w, smem + D_WHI, tid, D_THREADS);
     if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
     if (t == 0) umma::mbar_init(mbar, 1);
     umma::fence_before_sync();
@@ -555,8 +556,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
     if (tid == 0) small[8] = a.p.s2_b[0];
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = *tslot + (uint32_t)half * 128u;             // this pipeline's [TR x 80] fp32 accumulator
-    const uint32_t whi = umma::smem_u32(smem + D_WHI), wlo = umma::smem_u32(smem + D_WLO);
+    const uint32_t tmem = *tslot + (uint32_t)half * 256u;             // this pipeline's [TR x 160] fp32 accumulator
+    const uint32_t wop = umma::smem_u32(smem + D_WHI);
     const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
     // epilogue geometry. TR = 128: 16 warps = 4 TMEM lane quarters x 4 blocks of 16 columns, lane == tile row.
     // TR = 64 (measured with tools/umma_m64_probe.cu): rows 16q .. 16q+15 live in lanes 0..15 of quarter q, so 8 warps =
@@ -629,10 +630,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float4 hi, lo;
-                umma::tf32_split4(sreg[i], hi, lo);
-                sts4(Xs, off0 + i * PASS, hi);
-                sts4(Ls, off0 + i * PASS, lo);
+                sts4(Xs, off0 + i * PASS, sreg[i]);                          // raw fp32 = hi operand (the tensor core truncates)
+                sts4(Ls, off0 + i * PASS, umma::tf32_trunc_lo4(sreg[i]));
             }
             umma::fence_proxy_async();
             if (t == 0) *row_ctr = 0;
@@ -649,7 +648,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         GN_TICK(0)
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         const bool do_g1 = !(a.dbg & 16), do_g2 = !(a.dbg & 8);       // timing experiments only
-        if (do_g1 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (do_g1 && t == 0) umma::issue_split_gemm160<TR>(tmem, mbar, wop, xs_addr, ls_addr);
         // rows longer than HUB_DEG are summed by the whole pipeline in P3a (in-order relay): mark them while the GEMM runs
         if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
         if (do_g1) { umma::mbar_wait_suspend(mbar, phase); phase ^= 1; }        // hardware-suspended wait (no spinning)
@@ -659,7 +658,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             for (int cb = 0; cb < NCB; ++cb) {
                 const int c16 = NCB * cq + cb;                        // 16-column block
                 float v[16];
-                umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * c16, v);
+                umma::tmem_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + 16 * c16, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c16 + 4 * j);
@@ -671,7 +670,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             }
             if (cq == 0) {
                 float hv[4];
-                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                umma::tmem_ld4_sum(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
                 if (erow_ok) *reinterpret_cast<float4*>(hs_s + 4 * erow) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
         }
@@ -845,10 +844,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
                     if (!RF) stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
                     }
-                    float4 hi, lo;
-                    umma::tf32_split4(in_, hi, lo);              // operand of GEMM2
-                    sts4(Xs, off0 + it * PASS, hi);
-                    sts4(Ls, off0 + it * PASS, lo);
+                    sts4(Xs, off0 + it * PASS, in_);             // operand of GEMM2 (raw = hi, truncation split)
+                    sts4(Ls, off0 + it * PASS, umma::tf32_trunc_lo4(in_));
                     if (dec) {                                   // partial linear3 products of R_k (RF: of I'_k) over this lane's 4 channels
                         const float4 dv = RF ? ipo : rv;
                         hv0 = dot4(dv, w30); hv1 = dot4(dv, w31); hv2 = dot4(dv, w32); hv3 = dot4(dv, w33);
@@ -876,7 +873,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         GN_TICK(4)
         // ---- P4: GEMM2 || metadata of the next tile (one thread of the idle warp 15) || softmax of the input state ;
         //      I' epilogue (+ hid(I_{k+1}))
-        if (do_g2 && t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (do_g2 && t == 0) umma::issue_split_gemm160<TR>(tmem, mbar, wop, xs_addr, ls_addr);
         if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
         if (RF && t < nrows) {
@@ -910,7 +907,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             for (int cb = 0; cb < NCB; ++cb) {
                 const int c16 = NCB * cq + cb;                        // 16-column block
                 float v[16];
-                umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * c16, v);
+                umma::tmem_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + 16 * c16, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * c16 + 4 * j);
@@ -922,7 +919,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
             }
             if (cq == 0) {
                 float hv[4];
-                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                umma::tmem_ld4_sum(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
                 if (erow_ok && erow < nrows) *reinterpret_cast<float4*>(a.hid_i + (size_t)(tile0 + erow) * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
         }
@@ -1070,7 +1067,7 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
 // with LDG-fed operands (round 1; also the fallback when no tensor map can be encoded), 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
-    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 6) : 5; }
+    if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 12) : 5; }
     return g_step_kernel;
 }
 
@@ -1112,7 +1109,17 @@ static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t str
             const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
 #define GN_SS(O) (fast ? (rf ? launch_step_stream<true, true, O>(b, a, stream) : launch_step_stream<true, false, O>(b, a, stream)) \
                        : (rf ? launch_step_stream<false, true, O>(b, a, stream) : launch_step_stream<false, false, O>(b, a, stream)))
-            return step_kernel_choice() == 6 ? GN_SS(0) : GN_SS(1);
+#ifdef GNODE_ABLATIONS                                           // timing-only kernels (wrong numerics): tools/ab_bench.py kernel=7..9
+            if (fast && rf && a.n_steps == 0) {
+                if (step_kernel_choice() == 7) return launch_step_stream<true, true, 97>(b, a, stream);   // N = 160, 3xTF32, truncation split
+                if (step_kernel_choice() == 8) return launch_step_stream<true, true, 69>(b, a, stream);   // no MMAs
+                if (step_kernel_choice() == 9) return launch_step_stream<true, true, 73>(b, a, stream);   // no lo-operand pass
+                if (step_kernel_choice() == 10) return launch_step_stream<true, true, 17>(b, a, stream);  // round 2h: N = 80 operands, 32 MMAs per GEMM, rna split
+                if (step_kernel_choice() == 11) return launch_step_stream<true, true, 1>(b, a, stream);   // N = 160, 4 terms, rna split packed in place
+                if (step_kernel_choice() == 12) return launch_step_stream<true, true, 33>(b, a, stream);  // N = 160, 3xTF32, rna split
+            }
+#endif
+            return step_kernel_choice() == 6 ? GN_SS(64) : GN_SS(65);
 #undef GN_SS
         }
         if (a.hid_r != nullptr) return (var & VAR_FASTSIG) ? launch_step_dual<true, 2, true>(b, a, stream) : launch_step_dual<false, 2, true>(b, a, stream);
@@ -1169,6 +1176,9 @@ extern "C" int gnode_set_variant(int variant) {
 }
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
+#ifdef GNODE_ABLATIONS
+    if (kernel >= 7 && kernel <= 12) { g_step_kernel = kernel; return GNODE_OK; }
+#endif
     if (kernel < 0 || kernel > 6 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5 or 6"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;

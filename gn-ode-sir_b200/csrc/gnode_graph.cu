@@ -311,6 +311,41 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
         GN_CUDA(cudaMemcpy(b->d_tile_meta, tm.data(), sizeof(int4) * tm.size(), cudaMemcpyHostToDevice));
         GN_CUDA(cudaMalloc(&b->d_sub_meta, sizeof(int4) * sm.size()));
         GN_CUDA(cudaMemcpy(b->d_sub_meta, sm.data(), sizeof(int4) * sm.size(), cudaMemcpyHostToDevice));
+        // Row pairs of the neighbour gather (step_stream_kernel). A warp sums two rows side by side and both half-warps run
+        // the trip count of the longer row (padding slots read the all-zero row), so the two rows of a pair should have
+        // the same degree: the tile's rows are sorted by degree (counting sort) and slot 2p / 2p+1 take neighbours in that
+        // order. Tiles whose CSR slice fits the staged window stride the pairs over the 16 warps (pair p -> warp p % 16):
+        // the sorted pairs are dealt out in snake order so that every warp gets short and long pairs; hub tiles draw
+        // pairs from a ticket counter, longest first. The sums themselves do not depend on the pairing.
+        std::vector<uint8_t> perm((size_t)b->n_tiles * TILE);
+        std::vector<int32_t> key(TILE), start(258);
+        std::vector<uint8_t> sorted(TILE);
+        const bool no_pair_sort = getenv("GNODE_NO_PAIR_SORT") != nullptr;                     // A/B switch: rows 2p, 2p+1 as they come
+        for (int32_t t = 0; t < b->n_tiles; ++t) {
+            uint8_t* pm = perm.data() + (size_t)t * TILE;
+            for (int r = 0; r < TILE; ++r) pm[r] = (uint8_t)r;
+            if (!(tm[t].w & 1) || no_pair_sort) continue;
+            const int32_t ii = tm[t].z;
+            const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
+            const int64_t r0 = (int64_t)t * TILE - inst[ii].row0, nr = std::min<int64_t>(TILE, M - (int64_t)t * TILE);
+            std::fill(start.begin(), start.end(), 0);
+            for (int r = 0; r < TILE; ++r) {
+                key[r] = r < nr ? std::min<int32_t>(rp[r0 + r + 1] - rp[r0 + r], 255) : 256;     // rows past the end last
+                start[key[r] + 1]++;
+            }
+            for (int k = 1; k < 258; ++k) start[k] += start[k - 1];
+            for (int r = 0; r < TILE; ++r) sorted[start[key[r]]++] = (uint8_t)r;              // ascending degree, stable
+            const bool strided = tm[t].y <= 1536;
+            for (int p = 0; p < TILE / 2; ++p) {
+                int q;                                                                         // sorted pair taken by pair slot p
+                if (strided) { const int j = p / 16, w = p % 16; q = 16 * j + ((j & 1) ? 15 - w : w); }
+                else q = (int)(nr + 1) / 2 - 1 - p;                                            // longest pair first
+                if (q < 0) q = p;                                                              // slots past the tile's rows
+                pm[2 * p] = sorted[2 * q]; pm[2 * p + 1] = sorted[2 * q + 1];
+            }
+        }
+        GN_CUDA(cudaMalloc(&b->d_tile_perm, perm.size()));
+        GN_CUDA(cudaMemcpy(b->d_tile_perm, perm.data(), perm.size(), cudaMemcpyHostToDevice));
     }
     return GNODE_OK;
     };
@@ -330,6 +365,7 @@ extern "C" int gnode_batch_destroy(gnode_batch_t b) {
     cudaFree(b->d_sched);
     cudaFree(b->d_tile_meta);
     cudaFree(b->d_sub_meta);
+    cudaFree(b->d_tile_perm);
     delete b;
     return GNODE_OK;
 }

@@ -1,16 +1,24 @@
 // step_stream_kernel: the fused Euler step with the contiguous S_k stream fed by TMA (included by gnode_forward.cu).
 //
 // Same tile pipeline as step_dual_kernel (one 1024-thread CTA per SM = two 512-thread pipelines of 128-row tiles that
-// share the [W; W3] operand), with three changes that take bytes and LSU work out of the step:
+// share the [W; W3] operand), with these changes that take bytes and LSU work out of the step:
 //   * the S_k tile of the NEXT tile is fetched by two TMA tensor loads (cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of
 //     32 x 128 fp32, SASS UTMALDG) issued by the otherwise idle metadata thread as soon as GEMM2 of the current tile
 //     has finished reading the operand buffer: no registers, no LSU wavefronts and no L1 lines for this stream, and the
 //     load's latency hides behind the I' epilogue and the tile turn-over;
-//   * the tile lands directly in the canonical UMMA K-major operand layout and BECOMES the `hi` operand in place:
-//     tcgen05.mma kind::tf32 reads only the top 19 bits of each 32-bit element, so a word whose top bits are
-//     rna_tf32(x) and whose low 13 bits are those of x is hi to the tensor core and still x (exactly) to the row update
-//     that reads S_k from it later (tf32_pack / tf32_unpack): S_k is read from HBM/L2 ONCE per step (step_dual_kernel:
-//     twice), and the split product is bitwise the LDG-fed kernel's;
+//   * the tile lands directly in the canonical UMMA K-major operand layout and IS the `hi` operand: tcgen05.mma kind::tf32
+//     reads only the top 19 bits of each 32-bit element (tools/umma_lowbits_probe.cu), i.e. the raw fp32 word is
+//     hi = trunc_tf32(x) to the tensor core and still x to the row update that reads S_k from the same tile later. Nothing
+//     is converted or written back; the threads only add lo = rna_tf32(x - hi) in the second tile (truncation split,
+//     |x - hi - lo| <= 2^-21 |x|). S_k is read from HBM/L2 ONCE per step (step_dual_kernel: twice). The rna split packed in
+//     place (round 2h: hi = rna_tf32(x) in the top bits, the low 13 bits of x kept: tf32_pack / tf32_unpack) stays as an A/B
+//     variant: one more shared-memory store per element, +3 % time for half the split residual;
+//   * [W; W3] is ONE B operand with its hi and lo parts stacked along N (N = 160, umma::issue_split_gemm160): every A tile
+//     is read from shared memory once per GEMM instead of twice, 16 MMAs instead of 32. The tensor core fetches operands
+//     over the shared-memory port the LSU uses: without any MMA the step is 12 % faster, with the stacked operand 2.7 %
+//     (profiles/r2n_ab_ablations.log, r2o_ab_gemm_variants.log);
+//   * the rows of a tile are gathered in degree-sorted pairs (gnode_batch_create: tile_perm), so the two half-warps of a
+//     warp run the same trip count and few padding slots read the all-zero row (+1 %);
 //   * the neighbour sum is folded into S' in place (AI * S', the first product of dS, ode_nn_ngraph_sim.py:75), so the
 //     parked value needs no buffer of its own. (Measured and rejected: the gathering half-warp performing the whole row
 //     update with its own I_k / I'_k rows requested together with the neighbour rows -- 1.64e9 vs 1.66e9 node-steps/s,
@@ -39,9 +47,10 @@ struct StreamCfg {
     static constexpr int P_HS = P_RP + TR * 4 + 32;        // hid(S_k) [TR][4]
     static constexpr int P_HR = P_HS + TR * 16;            // hid(R_k) / W3 I'_k [TR][4]
     static constexpr int P_CI = P_HR + TR * 16;            // colidx slice + 64 B over-read pad
-    static constexpr int P_BYTES = ((P_CI + CAP * 4 + 64 + 1023) / 1024) * 1024;
+    static constexpr int P_PM = P_CI + CAP * 4 + 64;       // gather slot -> tile row (128 B, degree-sorted row pairs)
+    static constexpr int P_BYTES = ((P_PM + TR + 1023) / 1024) * 1024;
     static constexpr int TOTAL = D_SHARED + 2 * P_BYTES + 1024;
-    static constexpr int TMEM_COLS = 256;
+    static constexpr int TMEM_COLS = 512;                 // two [128 x 160] fp32 accumulators, 256 columns apart
     static_assert(TOTAL + 1024 <= 200704, "stay inside the 196 KB shared-memory carve-out (60 KB of L1 left)");
     static __device__ __forceinline__ int sw(int r, int c4) { return (c4 >> 3) * KBLK + (r << 7) + (((c4 & 7) ^ (r & 7)) << 4); }
 };
@@ -143,6 +152,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     float* hr_s = reinterpret_cast<float*>(hb + C::P_HR);
     int* ci_s = reinterpret_cast<int*>(hb + C::P_CI);
     unsigned* hub_mask = reinterpret_cast<unsigned*>(rp_s + TR + 2);
+    const unsigned char* pm_s = hb + C::P_PM;
     const int bar_id = 1 + half;
 #define HSYNC() umma::bar_sync(bar_id, PT)
 
@@ -190,7 +200,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         }
     };
 
-    umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
+    constexpr bool N160 = (OPT & 16) == 0;                            // OPT bit 4: the N = 80 operands of round 2h (A/B baseline)
+    if (N160) umma::prepare_weights160(a.p.lin_w, a.p.l3_w, smem + D_WHI, tid, D_THREADS);
+    else umma::prepare_weights80(a.p.lin_w, a.p.l3_w, smem + D_WHI, smem + D_WLO, tid, D_THREADS);
     if (tid < 32) umma::tmem_alloc(tslot, C::TMEM_COLS);
     if (t == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(sbar, (OPT & 1) ? 2 : 1); }
     umma::fence_before_sync();
@@ -200,9 +212,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     if (tid == 0) small[8] = a.p.s2_b[0];
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = *tslot + (uint32_t)half * 128u;             // this pipeline's [128 x 80] fp32 accumulator
-    const uint32_t whi = umma::smem_u32(smem + D_WHI), wlo = umma::smem_u32(smem + D_WLO);
+    const uint32_t tmem = *tslot + (uint32_t)half * 256u;             // this pipeline's [128 x 160] fp32 accumulator
+    const uint32_t wop = umma::smem_u32(smem + D_WHI);
     const uint32_t xs_addr = umma::smem_u32(Xs), ls_addr = umma::smem_u32(Ls);
+    // one thread: the split product of the operand tiles (hi in Xs, lo in Ls) with [W; W3]. OPT bits 1, 2, 4, 5 are A/B and
+    // timing variants (GNODE_ABLATIONS builds): 16 of the MMAs skipped / none issued / N = 80 operands / lo x lo term dropped
+    auto issue_gemm = [&]() {
+        if (OPT & 4) umma::mma_commit(mbar);
+        else if (OPT & 32) umma::issue_split_gemm160_3term<TR>(tmem, mbar, wop, xs_addr, ls_addr);
+        else if (N160) umma::issue_split_gemm160<TR, (OPT & 2) ? 1 : 0>(tmem, mbar, wop, xs_addr, ls_addr);
+        else umma::issue_split_gemm80<TR, (OPT & 2) ? 2 : 0>(tmem, mbar, wop, wop + umma::WB80_BYTES, xs_addr, ls_addr);
+    };
     const int q = warp & 3, cq = warp >> 2;                           // TMEM lane quarter, 16-column block
     const int erow = q * 32 + lane;                                   // tile row this thread owns in the epilogues
     uint32_t phase = 0, sphase = 0;
@@ -263,6 +283,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         {
             int rpv = 0, civ[3] = {0, 0, 0};
             float bgv = 0.f;
+            uint32_t pmv = 0;
+            if (single && t < TR / 4) pmv = __ldg(reinterpret_cast<const uint32_t*>(a.bv.tile_perm) + (size_t)(tile0 / TR) * (TR / 4) + t);
             const int ecnt = min(m.ecnt, C::CAP);
             if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
             if (single) {
@@ -273,7 +295,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
             umma::mbar_wait(sbar, sphase); sphase ^= 1;               // the S_k tile has landed in Xs
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < ((OPT & 8) ? 0 : 4); ++i) {
+                if (OPT & 64) { sts4(Ls, off0 + i * PASS, umma::tf32_trunc_lo4(lds4(Xs, off0 + i * PASS))); continue; }
                 float4 lo;
                 const float4 pk = tf32_pack4(lds4(Xs, off0 + i * PASS), lo);
                 sts4(Xs, off0 + i * PASS, pk);
@@ -283,6 +306,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (t == 0) *row_ctr = 0;
             if (t < TR / 32) hub_mask[t] = 0u;
             if (single && t <= nrows) rp_s[t] = rpv;
+            if (single && t < TR / 4) reinterpret_cast<uint32_t*>(hb + C::P_PM)[t] = pmv;
             if (single) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = civ[u];   // instance-local ids
@@ -292,7 +316,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         }
         HSYNC();                                                                // S1
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
-        if (t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (t == 0) issue_gemm();
         if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
         // row pairs of the neighbour gather: strided over the warps when the tile's CSR slice fits the staged window,
         // shared-memory tickets for hub tiles so that a long row does not leave the other warps idle
@@ -307,7 +331,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             return __shfl_sync(0xffffffffu, pp, 0);
         };
         auto gather_pair = [&](int p, int& rr, bool& ok) -> float4 {
-            rr = 2 * p + (lane >> 4);
+            rr = pm_s[2 * p + (lane >> 4)];                  // the pair's rows have (nearly) the same degree
             int e_rel = 0, deg = 0;
             if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = rp_s[rr + 1] - rp_s[rr]; }
             const bool hubrow = relay && deg > C::HUB_DEG;                 // summed by the in-order relay below
@@ -322,7 +346,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         umma::fence_after_sync();
         {
             float v[16];
-            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+            if (N160) umma::tmem_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v); else umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
@@ -333,7 +357,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
             if (cq == 0) {
                 float hv[4];
-                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                if (N160) umma::tmem_ld4_sum(tmem + ((uint32_t)(q * 32) << 16) + 64, hv); else umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
                 *reinterpret_cast<float4*>(hs_s + 4 * erow) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
         }
@@ -359,7 +383,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (ok) {
                 const int o = C::sw(rr, l);
                 const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
-                const float4 s = tf32_unpack4(lds4(Xs, o));
+                const float4 s = (OPT & 64) ? lds4(Xs, o) : tf32_unpack4(lds4(Xs, o));
                 const float nbe = -bg_s[rr], ga = bg_s[TR + rr];
                 float4 sn, in_, rn;
 #define GN_COMP(c)                                                                  \
@@ -377,7 +401,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
                 if (!RF) stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
                 float4 ilo;
-                sts4(Xs, o, tf32_pack4(in_, ilo));                   // hi operand of GEMM2 (packed like the S tile)
+                if (OPT & 64) { sts4(Xs, o, in_); ilo = umma::tf32_trunc_lo4(in_); }
+                else sts4(Xs, o, tf32_pack4(in_, ilo));              // hi operand of GEMM2 (packed like the S tile)
                 sts4(Ls, o, ilo);
                 if (dec) {
                     const float4 dv = RF ? ipo : rv;
@@ -522,7 +547,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         umma::fence_proxy_async();
         HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         // ---- P4: GEMM2 || metadata of the next tile || softmax of the input state ; I' epilogue (+ hid(I_{k+1}))
-        if (t == 0) umma::issue_split_gemm80<TR>(tmem, mbar, whi, wlo, xs_addr, ls_addr);
+        if (t == 0) issue_gemm();
         if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
         if (RF && t < nrows) {
@@ -552,7 +577,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         if (t == PT - 32) issue_s_load();                // GEMM2 has read Xs: the next tile's S_k rows may land there
         {
             float v[16];
-            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+            if (N160) umma::tmem_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v); else umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
@@ -563,7 +588,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
             if (cq == 0) {
                 float hv[4];
-                umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
+                if (N160) umma::tmem_ld4_sum(tmem + ((uint32_t)(q * 32) << 16) + 64, hv); else umma::tmem_ld4(tmem + ((uint32_t)(q * 32) << 16) + 64, hv);
                 if (erow < nrows) *reinterpret_cast<float4*>(a.hid_i + (size_t)(tile0 + erow) * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
         }

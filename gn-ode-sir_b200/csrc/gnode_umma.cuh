@@ -124,6 +124,16 @@ __device__ __forceinline__ void tf32_split4(float4 x, float4& hi, float4& lo) {
     tf32_split(x.x, hi.x, lo.x); tf32_split(x.y, hi.y, lo.y); tf32_split(x.z, hi.z, lo.z); tf32_split(x.w, hi.w, lo.w);
 }
 
+// Truncation split (the pipelined step kernels): tcgen05.mma kind::tf32 reads only the top 19 bits of a 32-bit element
+// (tools/umma_lowbits_probe.cu), so a raw fp32 word IS the operand hi = trunc_tf32(x): nothing is converted or written
+// back. lo = rna_tf32(x - hi); x - hi has up to 13 significant bits, so |x - hi - lo| <= 2^-21 |x| (rna split: 2^-22).
+__device__ __forceinline__ float tf32_trunc_lo(float x) {
+    return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+__device__ __forceinline__ float4 tf32_trunc_lo4(float4 x) {
+    return make_float4(tf32_trunc_lo(x.x), tf32_trunc_lo(x.y), tf32_trunc_lo(x.z), tf32_trunc_lo(x.w));
+}
+
 // byte offset of chunk c4 of row n in the 64-row B operand (K-block stride 8 KB)
 __device__ __forceinline__ int swb_off(int n, int c4) { return ((c4 >> 3) << 13) + (n << 7) + (((c4 & 7) ^ (n & 7)) << 4); }
 
@@ -195,13 +205,13 @@ __device__ __forceinline__ void prepare_weights80(const float* __restrict__ W, c
 
 // One thread: D[TR x 80] (TMEM columns tmem .. tmem+79) = X [W; W3]^T as the 4-term split product, then commit.
 // TR = UMMA M = 128 or 64; the A operand's K-block stride is TR * 128 B.
-template <int TR>
+template <int TR, int P0 = 0>      // P0 > 0: timing ablations only (passes skipped, wrong numerics)
 __device__ __forceinline__ void issue_split_gemm80(uint32_t tmem, uint64_t* bar, uint32_t whi, uint32_t wlo, uint32_t xhi, uint32_t xlo) {
     fence_after_sync();
     constexpr uint32_t idesc = instr_desc_tf32(TR, NB80);
     uint32_t acc = 0;
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = P0; pass < 4; ++pass) {
         const uint32_t abase = (pass < 2) ? xlo : xhi;
         const uint32_t bbase = (pass == 0 || pass == 2) ? wlo : whi;
 #pragma unroll
@@ -213,6 +223,103 @@ __device__ __forceinline__ void issue_split_gemm80(uint32_t tmem, uint64_t* bar,
         }
     }
     mma_commit(bar);
+}
+
+// ---- N = 160 variant (the pipelined step kernels): the hi and the lo part of [W; W3] are stacked along N (rows 0..79 hi,
+// rows 80..159 lo of ONE B operand), so a pass over an A tile produces A Whi^T in accumulator columns 0..79 and A Wlo^T
+// in columns 80..159: the 4-term split product takes 16 MMAs of M128 N160 K8 (X lo pass, then X hi pass) instead of 32
+// of N80, and every A tile is read from shared memory once per GEMM instead of twice (144 KB of operand reads per GEMM
+// instead of 208 KB -- the tensor core fetches its operands over the same shared-memory port the LSU uses, and
+// removing the MMAs altogether is worth 17 % of the step, profiles/r2n_ab_ablations.log). The epilogue adds the two
+// column blocks (small part first). K-block stride of the 160-row operand: 160 * 128 B.
+constexpr int NB160 = 160;
+constexpr int WB160_KBLOCK = NB160 * 128;          // 20480 B (1024-B aligned)
+constexpr int WB160_BYTES = 2 * WB160_KBLOCK;      // 40960 B = the hi and lo operands of the N = 80 variant together
+__device__ __forceinline__ int swb160_off(int n, int c4) { return (c4 >> 3) * WB160_KBLOCK + (n << 7) + (((c4 & 7) ^ (n & 7)) << 4); }
+
+__device__ __forceinline__ void prepare_weights160(const float* __restrict__ W, const float* __restrict__ W3, unsigned char* Wop,
+                                                   int tid, int nthreads) {
+    for (int idx = tid; idx < NB80 * CHUNKS; idx += nthreads) {
+        const int n = idx >> 4, c4 = idx & 15;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+        if (n < H) x = ldg4(W + n * H + 4 * c4);
+        else if (n < H + 4) x = ldg4(W3 + (n - H) * H + 4 * c4);
+        tf32_split4(x, hi, lo);
+        sts4(Wop, swb160_off(n, c4), hi);
+        sts4(Wop, swb160_off(NB80 + n, c4), lo);
+    }
+    fence_proxy_async();
+}
+
+// One thread: one pass of 8 MMAs (M = TR, N = 160, K = 8) of the A tile at `abase` over the stacked operand; `fresh` = the
+// first MMA overwrites the accumulator.
+template <int TR>
+__device__ __forceinline__ void issue_pass160(uint32_t tmem, uint32_t wop, uint32_t abase, bool fresh) {
+    constexpr uint32_t idesc = instr_desc_tf32(TR, NB160);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t aoff = (uint32_t)(k >> 2) * (TR * 128) + ((k & 3) << 5);
+        const uint32_t boff = (uint32_t)(k >> 2) * WB160_KBLOCK + ((k & 3) << 5);
+        mma_tf32(tmem, smem_desc(abase + aoff), smem_desc(wop + boff), idesc, (fresh && k == 0) ? 0u : 1u);
+    }
+}
+// One thread: TMEM columns tmem .. tmem+79 = X Whi^T, tmem+80 .. tmem+159 = X Wlo^T with X = Xlo + Xhi (small pass first),
+// then commit. P0 > 0: timing ablation only (lo pass skipped, wrong numerics). (Issuing the hi pass of GEMM1 early, while
+// the threads still compute the lo operand, was measured: no gain, and big-before-small accumulation costs accuracy.)
+template <int TR, int P0 = 0>
+__device__ __forceinline__ void issue_split_gemm160(uint32_t tmem, uint64_t* bar, uint32_t wop, uint32_t xhi, uint32_t xlo) {
+    fence_after_sync();
+    if (P0 == 0) issue_pass160<TR>(tmem, wop, xlo, true);
+    issue_pass160<TR>(tmem, wop, xhi, P0 != 0);
+    mma_commit(bar);
+}
+
+// A/B variant: the lo x lo term dropped (3xTF32). X hi pass over the N = 160 operand first (its first MMA overwrites all
+// 160 columns), then the X lo pass over the hi rows only (N = 80, columns 0..79).
+template <int TR>
+__device__ __forceinline__ void issue_split_gemm160_3term(uint32_t tmem, uint64_t* bar, uint32_t wop, uint32_t xhi, uint32_t xlo) {
+    fence_after_sync();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t abase = pass == 0 ? xhi : xlo;
+        const uint32_t idesc = pass == 0 ? instr_desc_tf32(TR, NB160) : instr_desc_tf32(TR, NB80);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t aoff = (uint32_t)(k >> 2) * (TR * 128) + ((k & 3) << 5);
+            const uint32_t boff = (uint32_t)(k >> 2) * WB160_KBLOCK + ((k & 3) << 5);
+            mma_tf32(tmem, smem_desc(abase + aoff), smem_desc(wop + boff), idesc, acc);
+            acc = 1;
+        }
+    }
+    mma_commit(bar);
+}
+
+// 16 (4) accumulator columns of this thread's TMEM lane, summed over the two column blocks of the N = 160 product:
+// v = (X Wlo^T)[c] + (X Whi^T)[c]
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16], s[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]),
+                   "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
+                 : "r"(taddr + (uint32_t)NB80));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__uint_as_float(s[i]), __uint_as_float(r[i]));
+}
+__device__ __forceinline__ void tmem_ld4_sum(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4], s[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]) : "r"(taddr + (uint32_t)NB80));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __fadd_rn(__uint_as_float(s[i]), __uint_as_float(r[i]));
 }
 
 __device__ __forceinline__ void issue_split_gemm(const Ctx& cx, uint32_t xhi, uint32_t xlo) {

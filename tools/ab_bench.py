@@ -3,7 +3,10 @@ events): interleaves the configurations given on the command line and prints nod
 
     python tools/ab_bench.py [--trials 64] [--rounds 3] r_state=0 r_state=1 dbg=1048576 ...
 Each configuration is a comma-separated list of key=value: r_state (gnode_set_r_state), dbg (env GNODE_DBG, read per
-rollout), kernel (gnode_set_step_kernel), variant (gnode_set_variant: 0 = FFMA + expf, the reference's arithmetic)."""
+rollout), kernel (gnode_set_step_kernel), variant (gnode_set_variant: 0 = FFMA + expf, the reference's arithmetic).
+A library built with -DGNODE_ABLATIONS (_build.build_library(force=True, extra_flags=["-DGNODE_ABLATIONS"])) adds the
+A/B kernels 7 = 3xTF32 (lo x lo dropped), 10 = round-2h operands (N = 80, rna split packed in place), 11 = N = 160 with
+the rna split, 12 = 11 with 3xTF32, and the timing-only 8 = no MMAs, 9 = no lo-operand pass (wrong numerics)."""
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
