@@ -91,7 +91,7 @@ struct gnode_batch {
     int2* d_sched = nullptr;         // [n_tiles] by sequence number: {tile, first row of the look-ahead I' prefetch or -1}
     int4* d_tile_meta = nullptr;     // [n_tiles] {first CSR entry, entry count, owning instance, bit 0: inside one instance, bit 1: hub relay}
     int4* d_sub_meta = nullptr;      // [2 n_tiles] the same for the two 64-row halves of every tile
-    uint8_t* d_tile_perm = nullptr;  // [n_tiles][128] gather slot -> tile row: rows of similar degree share a warp (row pairs)
+    uint8_t* d_tile_perm = nullptr;  // [n_tiles][64][4] work items of the gather: tile rows {a, b | c, d} summed by one warp in one round trip
     int device = 0;
     int sm_count = 0;
     // captured reverse sweeps of launch-bound batches (gnode_rollout_backward): key of all arguments -> cudaGraphExec_t

@@ -311,37 +311,64 @@ extern "C" int gnode_batch_create(const gnode_graph_t* inst_graphs, int32_t n_in
         GN_CUDA(cudaMemcpy(b->d_tile_meta, tm.data(), sizeof(int4) * tm.size(), cudaMemcpyHostToDevice));
         GN_CUDA(cudaMalloc(&b->d_sub_meta, sizeof(int4) * sm.size()));
         GN_CUDA(cudaMemcpy(b->d_sub_meta, sm.data(), sizeof(int4) * sm.size(), cudaMemcpyHostToDevice));
-        // Row pairs of the neighbour gather (step_stream_kernel). A warp sums two rows side by side and both half-warps run
-        // the trip count of the longer row (padding slots read the all-zero row), so the two rows of a pair should have
-        // the same degree: the tile's rows are sorted by degree (counting sort) and slot 2p / 2p+1 take neighbours in that
-        // order. Tiles whose CSR slice fits the staged window stride the pairs over the 16 warps (pair p -> warp p % 16):
-        // the sorted pairs are dealt out in snake order so that every warp gets short and long pairs; hub tiles draw
-        // pairs from a ticket counter, longest first. The sums themselves do not depend on the pairing.
-        std::vector<uint8_t> perm((size_t)b->n_tiles * TILE);
-        std::vector<int32_t> key(TILE), start(258);
+        // Work items of the neighbour gather (step_stream_kernel): uint8 rows[64][4] per tile. A warp sums the rows
+        // {a, b} of an item in its lower half-warp and {c, d} in its upper one, all loads of the item in ONE memory round
+        // trip (at most 12 neighbour rows per lane), and both half-warps run the trip count of the longer side (padding
+        // slots read the all-zero row). So: the tile's rows are sorted by degree; rows with at most 6 neighbours go four
+        // to an item (two per half-warp, 6 + 6 slots: half as many round trips for them -- 47 % of the rows of a
+        // Barabasi-Albert graph with m = 5), the others two to an item with a neighbour of (nearly) the same degree
+        // (b = d = 0xFF). Tiles whose CSR slice fits the staged window stride the items over the 16 warps (warp w takes
+        // items w, w + 16, w + 32, w + 48): the items are dealt to the warps longest first, each to the warp with the
+        // fewest round trips so far (a row of degree d > 12 needs 1 + ceil((d - 12) / 8) of them). Hub tiles draw items from
+        // a ticket counter, longest first, and form no four-row items (their slice overflows the window). Unused item
+        // slots are 0xFF. The sums themselves do not depend on the grouping: every row is still added up alone, in
+        // ascending column order.
+        const bool no_sort = getenv("GNODE_NO_PAIR_SORT") != nullptr;                          // A/B: rows 2p, 2p+1 as they come
+        const bool no_quads = no_sort || getenv("GNODE_NO_QUADS") != nullptr;                  // A/B: two-row items only
+        std::vector<uint8_t> perm((size_t)b->n_tiles * 256, 0xFF);
+        std::vector<int32_t> deg(TILE), start(258);
         std::vector<uint8_t> sorted(TILE);
-        const bool no_pair_sort = getenv("GNODE_NO_PAIR_SORT") != nullptr;                     // A/B switch: rows 2p, 2p+1 as they come
+        struct Item { uint8_t r[4]; int32_t cost; };
+        std::vector<Item> items;
+        items.reserve(64);
+        auto rounds = [](int32_t d) { return d <= 12 ? 1 : 1 + (d - 12 + 7) / 8; };
         for (int32_t t = 0; t < b->n_tiles; ++t) {
-            uint8_t* pm = perm.data() + (size_t)t * TILE;
-            for (int r = 0; r < TILE; ++r) pm[r] = (uint8_t)r;
-            if (!(tm[t].w & 1) || no_pair_sort) continue;
+            uint8_t* out_items = perm.data() + (size_t)t * 256;
+            const int64_t nr = std::min<int64_t>(TILE, M - (int64_t)t * TILE);
+            if (!(tm[t].w & 1) || no_sort) {                                                   // rows as they come, two per item
+                for (int p = 0; p < TILE / 2; ++p) { out_items[4 * p] = (uint8_t)(2 * p); out_items[4 * p + 2] = (uint8_t)(2 * p + 1); }
+                continue;
+            }
             const int32_t ii = tm[t].z;
             const std::vector<int32_t>& rp = inst_graphs[ii]->h_rowptr;
-            const int64_t r0 = (int64_t)t * TILE - inst[ii].row0, nr = std::min<int64_t>(TILE, M - (int64_t)t * TILE);
+            const int64_t r0 = (int64_t)t * TILE - inst[ii].row0;
             std::fill(start.begin(), start.end(), 0);
-            for (int r = 0; r < TILE; ++r) {
-                key[r] = r < nr ? std::min<int32_t>(rp[r0 + r + 1] - rp[r0 + r], 255) : 256;     // rows past the end last
-                start[key[r] + 1]++;
-            }
+            for (int r = 0; r < nr; ++r) { deg[r] = rp[r0 + r + 1] - rp[r0 + r]; start[std::min(deg[r], 255) + 1]++; }
             for (int k = 1; k < 258; ++k) start[k] += start[k - 1];
-            for (int r = 0; r < TILE; ++r) sorted[start[key[r]]++] = (uint8_t)r;              // ascending degree, stable
+            for (int r = 0; r < nr; ++r) sorted[start[std::min(deg[r], 255)]++] = (uint8_t)r;   // ascending degree, stable
             const bool strided = tm[t].y <= 1536;
-            for (int p = 0; p < TILE / 2; ++p) {
-                int q;                                                                         // sorted pair taken by pair slot p
-                if (strided) { const int j = p / 16, w = p % 16; q = 16 * j + ((j & 1) ? 15 - w : w); }
-                else q = (int)(nr + 1) / 2 - 1 - p;                                            // longest pair first
-                if (q < 0) q = p;                                                              // slots past the tile's rows
-                pm[2 * p] = sorted[2 * q]; pm[2 * p + 1] = sorted[2 * q + 1];
+            items.clear();
+            int pos = 0;
+            if (strided && !no_quads)
+                for (; pos + 4 <= nr && deg[sorted[pos + 3]] <= 6; pos += 4)
+                    items.push_back(Item{{sorted[pos], sorted[pos + 1], sorted[pos + 2], sorted[pos + 3]}, 1});
+            for (; pos < nr; pos += 2) {
+                const bool two = pos + 1 < nr;
+                items.push_back(Item{{sorted[pos], 0xFF, two ? sorted[pos + 1] : (uint8_t)0xFF, 0xFF},
+                                     rounds(deg[two ? sorted[pos + 1] : sorted[pos]])});
+            }
+            std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
+            if (!strided) {                                                                    // tickets: longest first
+                for (size_t i = 0; i < items.size(); ++i) memcpy(out_items + 4 * i, items[i].r, 4);
+                continue;
+            }
+            int32_t load[16] = {0}, cnt[16] = {0};
+            for (const Item& it : items) {
+                int best = -1;
+                for (int w = 0; w < 16; ++w)
+                    if (cnt[w] < 4 && (best < 0 || load[w] < load[best])) best = w;
+                memcpy(out_items + 4 * (best + 16 * cnt[best]), it.r, 4);
+                load[best] += it.cost; cnt[best]++;
             }
         }
         GN_CUDA(cudaMalloc(&b->d_tile_perm, perm.size()));

@@ -17,8 +17,9 @@
 //     is read from shared memory once per GEMM instead of twice, 16 MMAs instead of 32. The tensor core fetches operands
 //     over the shared-memory port the LSU uses: without any MMA the step is 12 % faster, with the stacked operand 2.7 %
 //     (profiles/r2n_ab_ablations.log, r2o_ab_gemm_variants.log);
-//   * the rows of a tile are gathered in degree-sorted pairs (gnode_batch_create: tile_perm), so the two half-warps of a
-//     warp run the same trip count and few padding slots read the all-zero row (+1 %);
+//   * the rows of a tile are gathered in degree-sorted groups (gnode_batch_create: tile_perm): the two half-warps of a warp
+//     run the same trip count and few padding slots read the all-zero row, and rows with at most 6 neighbours are summed
+//     two per half-warp in one memory round trip;
 //   * the neighbour sum is folded into S' in place (AI * S', the first product of dS, ode_nn_ngraph_sim.py:75), so the
 //     parked value needs no buffer of its own. (Measured and rejected: the gathering half-warp performing the whole row
 //     update with its own I_k / I'_k rows requested together with the neighbour rows -- 1.64e9 vs 1.66e9 node-steps/s,
@@ -47,8 +48,8 @@ struct StreamCfg {
     static constexpr int P_HS = P_RP + TR * 4 + 32;        // hid(S_k) [TR][4]
     static constexpr int P_HR = P_HS + TR * 16;            // hid(R_k) / W3 I'_k [TR][4]
     static constexpr int P_CI = P_HR + TR * 16;            // colidx slice + 64 B over-read pad
-    static constexpr int P_PM = P_CI + CAP * 4 + 64;       // gather slot -> tile row (128 B, degree-sorted row pairs)
-    static constexpr int P_BYTES = ((P_PM + TR + 1023) / 1024) * 1024;
+    static constexpr int P_PM = P_CI + CAP * 4 + 64;       // work items of the gather: [64] x {a, b | c, d} tile rows (256 B)
+    static constexpr int P_BYTES = ((P_PM + 256 + 1023) / 1024) * 1024;
     static constexpr int TOTAL = D_SHARED + 2 * P_BYTES + 1024;
     static constexpr int TMEM_COLS = 512;                 // two [128 x 160] fp32 accumulators, 256 columns apart
     static_assert(TOTAL + 1024 <= 200704, "stay inside the 196 KB shared-memory carve-out (60 KB of L1 left)");
@@ -111,6 +112,42 @@ __device__ __forceinline__ float4 gather_smem_zm(const float* __restrict__ lane_
     return acc;
 }
 
+// four-row item: the lane's chunks of two rows of at most D neighbours each, all 2 D loads in one round trip; each row is
+// summed alone in ascending column order (slots past its degree read the all-zero row: + 0 is exact)
+template <int D>
+__device__ __forceinline__ void gather_two_rows(const float* __restrict__ lane_base, const int* cpa, int da, const int* cpb, int db,
+                                                int zrow, uint64_t pol, float4& sa, float4& sb) {
+    float4 v[2 * D + 1];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int c = (k < da) ? cpa[k] : zrow;
+        v[k] = ldg4_hint(lane_base + (size_t)(unsigned)c * H, pol);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int c = (k < db) ? cpb[k] : zrow;
+        v[D + k] = ldg4_hint(lane_base + (size_t)(unsigned)c * H, pol);
+    }
+    sa = make_float4(0.f, 0.f, 0.f, 0.f); sb = sa;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { sa.x += v[k].x; sa.y += v[k].y; sa.z += v[k].z; sa.w += v[k].w; }
+#pragma unroll
+    for (int k = 0; k < D; ++k) { sb.x += v[D + k].x; sb.y += v[D + k].y; sb.z += v[D + k].z; sb.w += v[D + k].w; }
+}
+__device__ __forceinline__ void gather_quad(const float* __restrict__ lane_base, const int* cpa, int da, const int* cpb, int db,
+                                            int dmax, int zrow, uint64_t pol, float4& sa, float4& sb) {
+    sa = make_float4(0.f, 0.f, 0.f, 0.f); sb = sa;
+    switch (dmax) {                                      // warp-uniform
+        case 6: gather_two_rows<6>(lane_base, cpa, da, cpb, db, zrow, pol, sa, sb); break;
+        case 5: gather_two_rows<5>(lane_base, cpa, da, cpb, db, zrow, pol, sa, sb); break;
+        case 4: gather_two_rows<4>(lane_base, cpa, da, cpb, db, zrow, pol, sa, sb); break;
+        case 3: gather_two_rows<3>(lane_base, cpa, da, cpb, db, zrow, pol, sa, sb); break;
+        case 2: gather_two_rows<2>(lane_base, cpa, da, cpb, db, zrow, pol, sa, sb); break;
+        case 1: gather_two_rows<1>(lane_base, cpa, da, cpb, db, zrow, pol, sa, sb); break;
+        default: break;
+    }
+}
+
 // per-step operands (persistent rollout: derived per Euler step by one thread)
 struct SStep {
     const float* y_in; float* y_out;
@@ -152,7 +189,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     float* hr_s = reinterpret_cast<float*>(hb + C::P_HR);
     int* ci_s = reinterpret_cast<int*>(hb + C::P_CI);
     unsigned* hub_mask = reinterpret_cast<unsigned*>(rp_s + TR + 2);
-    const unsigned char* pm_s = hb + C::P_PM;
+    const uint32_t* items_s = reinterpret_cast<const uint32_t*>(hb + C::P_PM);
     const int bar_id = 1 + half;
 #define HSYNC() umma::bar_sync(bar_id, PT)
 
@@ -284,7 +321,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             int rpv = 0, civ[3] = {0, 0, 0};
             float bgv = 0.f;
             uint32_t pmv = 0;
-            if (single && t < TR / 4) pmv = __ldg(reinterpret_cast<const uint32_t*>(a.bv.tile_perm) + (size_t)(tile0 / TR) * (TR / 4) + t);
+            if (single && t < 64) pmv = __ldg(reinterpret_cast<const uint32_t*>(a.bv.tile_perm) + (size_t)(tile0 / TR) * 64 + t);
             const int ecnt = min(m.ecnt, C::CAP);
             if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
             if (single) {
@@ -306,7 +343,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (t == 0) *row_ctr = 0;
             if (t < TR / 32) hub_mask[t] = 0u;
             if (single && t <= nrows) rp_s[t] = rpv;
-            if (single && t < TR / 4) reinterpret_cast<uint32_t*>(hb + C::P_PM)[t] = pmv;
+            if (single && t < 64) reinterpret_cast<uint32_t*>(hb + C::P_PM)[t] = pmv;
             if (single) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = civ[u];   // instance-local ids
@@ -318,20 +355,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         if (t == 0) issue_gemm();
         if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
-        // row pairs of the neighbour gather: strided over the warps when the tile's CSR slice fits the staged window,
-        // shared-memory tickets for hub tiles so that a long row does not leave the other warps idle
+        // work items of the neighbour gather (gnode_batch_create): strided over the warps when the tile's CSR slice fits the
+        // staged window, shared-memory tickets for hub tiles so that a long row does not leave the other warps idle
         const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
         const int zrow = a.ip_zrow - i_row0;                 // the all-zero row that follows the I' rows
         const bool static_rows = m.ecnt <= C::CAP;
         int sj = 0;
-        auto draw_pair = [&]() -> int {
-            if (static_rows) { const int pp = warp + (PT / 32) * sj; ++sj; return pp; }
-            int pp = 0;
-            if (lane == 0) pp = atomicAdd(row_ctr, 1);
-            return __shfl_sync(0xffffffffu, pp, 0);
+        auto draw_item = [&]() -> int {
+            if (static_rows) { const int it = sj < 4 ? warp + (PT / 32) * sj : 64; ++sj; return it; }
+            int it = 0;
+            if (lane == 0) it = atomicAdd(row_ctr, 1);
+            return __shfl_sync(0xffffffffu, it, 0);
         };
-        auto gather_pair = [&](int p, int& rr, bool& ok) -> float4 {
-            rr = pm_s[2 * p + (lane >> 4)];                  // the pair's rows have (nearly) the same degree
+        // two-row item: tile row rr of this half-warp (0xFF = none), one round trip per 12 neighbours
+        auto gather_pair = [&](int rr, bool& ok) -> float4 {
             int e_rel = 0, deg = 0;
             if (rr < nrows) { e_rel = rp_s[rr] - ebase; deg = rp_s[rr + 1] - rp_s[rr]; }
             const bool hubrow = relay && deg > C::HUB_DEG;                 // summed by the in-order relay below
@@ -425,21 +462,39 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         // what the gathering half-warp does with the finished neighbour sum of row rr: AI * S' replaces S' in place
         float* const ai_out = STP(ai_out);
         auto finish_row = [&](int rr, bool ok, float4 acc) {
+            if (!ok) return;                                 // rr may be 0xFF (no row): never form an address from it
             const int o = C::sw(rr, l);
             const float4 sp = lds4(Ls, o);
-            if (ai_out != nullptr && ok) stg4_hint(ai_out + (size_t)(tile0 + rr) * H + 4 * l, acc, pol_stream);
-            if (ok) sts4(Ls, o, make_float4(__fmul_rn(acc.x, sp.x), __fmul_rn(acc.y, sp.y), __fmul_rn(acc.z, sp.z), __fmul_rn(acc.w, sp.w)));
+            if (ai_out != nullptr) stg4_hint(ai_out + (size_t)(tile0 + rr) * H + 4 * l, acc, pol_stream);
+            sts4(Ls, o, make_float4(__fmul_rn(acc.x, sp.x), __fmul_rn(acc.y, sp.y), __fmul_rn(acc.z, sp.z), __fmul_rn(acc.w, sp.w)));
         };
 
         // ---- P3a: neighbour sums AI (sequential, ascending columns), folded into S' in place
         {
             if (single) {
-                int p = draw_pair();
-                while (p < TR / 2) {
-                    int rr; bool ok;
-                    const float4 acc = gather_pair(p, rr, ok);
-                    finish_row(rr, ok, acc);
-                    p = draw_pair();
+                int it = draw_item();
+                while (it < 64) {
+                    const uint32_t rw = items_s[it];                       // tile rows {a, b | c, d}, 0xFF = none
+                    if (rw == 0xFFFFFFFFu) break;                          // no more items (for this warp / in this tile)
+                    const uint32_t mine = rw >> ((lane & 16) ? 16 : 0);
+                    const int ra = (int)(mine & 0xFFu), rb = (int)((mine >> 8) & 0xFFu);
+                    if ((rw & 0xFF00FF00u) != 0xFF00FF00u) {               // four rows of at most 6 neighbours: one round trip
+                        const bool oka = ra < nrows, okb = rb < nrows;
+                        int ea = 0, da = 0, eb = 0, db = 0;
+                        if (oka) { ea = rp_s[ra] - ebase; da = rp_s[ra + 1] - rp_s[ra]; }
+                        if (okb) { eb = rp_s[rb] - ebase; db = rp_s[rb + 1] - rp_s[rb]; }
+                        int dmax = max(da, db);
+                        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, 16));
+                        float4 sa, sb;
+                        gather_quad(lane_base, ci_s + ea, da, ci_s + eb, db, dmax, zrow, pol_keep, sa, sb);
+                        finish_row(ra, oka, sa);
+                        finish_row(rb, okb, sb);
+                    } else {
+                        bool ok;
+                        const float4 acc = gather_pair(ra, ok);
+                        finish_row(ra, ok, acc);
+                    }
+                    it = draw_item();
                 }
                 // Hub rows: loads by the whole pipeline (256 neighbours per round trip), adds relayed from warp to warp in
                 // column order through shared memory -- bitwise the serial walk (see step_dual_kernel / DESIGN.md 3.1)
