@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
                     const size_t off = (size_t)g * H + 4 * l;
                     stg4_stream(a.y_out + off, s0);
                     stg4_stream(a.y_out + plane + off, i0);
-                    stg4_stream(a.y_out + 2 * plane + off, r0);
+                    if (a.hid_r == nullptr) stg4_stream(a.y_out + 2 * plane + off, r0);   // inference carries hid(R) only: no R plane
                 }
                 sts4(Xs, sw_off(rr, l), i0);
                 if (a.probs != nullptr || a.hid_i != nullptr || a.hid_r != nullptr)
@@ -1063,8 +1063,10 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
     return GNODE_OK;
 }
 
-// 5 = pipelined kernel with the TMA-fed S stream (default), 6 = 5 without the deferred store wait, 3 = the same pipeline
-// with LDG-fed operands (round 1; also the fallback when no tensor map can be encoded), 0 = generic
+// 5 = pipelined kernel with the TMA-fed S stream (default), 6 = 5 without the deferred store wait, 7 = 5 with 3xTF32 (the
+// lo x lo term of the 4-term split product dropped: +2 % speed, per-product error 2^-21 + 2^-21 instead of 2^-21 + 2^-22;
+// still inside the 1e-5 bar on every golden, tools/kernel_error_table.py), 3 = the same pipeline with LDG-fed operands
+// (round 1; also the fallback when no tensor map can be encoded), 0 = generic
 static int g_step_kernel = -1;
 static int step_kernel_choice() {
     if (g_step_kernel < 0) { const char* e = getenv("GNODE_STEP_KERNEL"); g_step_kernel = e ? std::min(std::max(atoi(e), 0), 12) : 5; }
@@ -1109,9 +1111,9 @@ static int launch_step(const gnode_batch* b, const StepArgs& a, cudaStream_t str
             const bool fast = (var & VAR_FASTSIG) != 0, rf = a.hid_r != nullptr;
 #define GN_SS(O) (fast ? (rf ? launch_step_stream<true, true, O>(b, a, stream) : launch_step_stream<true, false, O>(b, a, stream)) \
                        : (rf ? launch_step_stream<false, true, O>(b, a, stream) : launch_step_stream<false, false, O>(b, a, stream)))
-#ifdef GNODE_ABLATIONS                                           // timing-only kernels (wrong numerics): tools/ab_bench.py kernel=7..9
+            if (step_kernel_choice() == 7) return GN_SS(97);              // 3xTF32: the lo x lo term of the split product dropped
+#ifdef GNODE_ABLATIONS                                           // A/B and timing-only kernels: tools/ab_bench.py kernel=8..12
             if (fast && rf && a.n_steps == 0) {
-                if (step_kernel_choice() == 7) return launch_step_stream<true, true, 97>(b, a, stream);   // N = 160, 3xTF32, truncation split
                 if (step_kernel_choice() == 8) return launch_step_stream<true, true, 69>(b, a, stream);   // no MMAs
                 if (step_kernel_choice() == 9) return launch_step_stream<true, true, 73>(b, a, stream);   // no lo-operand pass
                 if (step_kernel_choice() == 10) return launch_step_stream<true, true, 17>(b, a, stream);  // round 2h: N = 80 operands, 32 MMAs per GEMM, rna split
@@ -1177,9 +1179,9 @@ extern "C" int gnode_set_variant(int variant) {
 extern "C" int gnode_get_variant(void) { return current_variant(); }
 extern "C" int gnode_set_step_kernel(int kernel) {
 #ifdef GNODE_ABLATIONS
-    if (kernel >= 7 && kernel <= 12) { g_step_kernel = kernel; return GNODE_OK; }
+    if (kernel >= 8 && kernel <= 12) { g_step_kernel = kernel; return GNODE_OK; }
 #endif
-    if (kernel < 0 || kernel > 6 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5 or 6"); return GNODE_ERR_ARG; }
+    if (kernel < 0 || kernel > 7 || kernel == 1 || kernel == 2 || kernel == 4) { set_error("gnode_set_step_kernel: kernel must be 0, 3, 5, 6 or 7"); return GNODE_ERR_ARG; }
     g_step_kernel = kernel;
     return GNODE_OK;
 }

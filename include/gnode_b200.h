@@ -79,8 +79,9 @@ int gnode_get_variant(void);
 /* Structure of the tensor-core step kernel (variants with bit 0 set): 5 = pipelined, S_k stream by TMA (default: one
  * 1024-thread CTA per SM running two 128-row tile pipelines that share the weight operand; the S_k tile arrives by TMA
  * tensor loads straight into the UMMA operand layout, the raw fp32 tile is the hi operand and S_k is read once; the
- * decoder's hidden layer comes out of the step's two GEMMs), 6 = 5 with a block barrier after the I' store, 3 = the same
- * pipeline with LDG-fed operands (round 1; also what runs when no tensor map can be encoded), 0 = generic.
+ * decoder's hidden layer comes out of the step's two GEMMs), 6 = 5 with a block barrier after the I' store, 7 = 5 with
+ * 3xTF32 (the lo x lo term of the 4-term split product dropped: ~2 % faster, per-product error 2^-20 instead of 1.5 * 2^-21),
+ * 3 = the same pipeline with LDG-fed operands (round 1; also what runs when no tensor map can be encoded), 0 = generic.
  * Default: env GNODE_STEP_KERNEL or 5. All produce the same trajectories within the parity tolerance.
  * These switches (variant, step kernel, R state, persistent) are PROCESS-WIDE settings read at every rollout call:
  * set them before launching work from several threads, not concurrently with it. */

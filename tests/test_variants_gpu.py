@@ -71,7 +71,7 @@ def test_variant_large_graph_fp64(gn, variant):
     assert err_ours <= max(1e-5, 2.0 * err_ref), (err_ours, err_ref)
 
 
-STEP_KERNELS = {5: "stream", 6: "stream-barrier", 3: "dual", 0: "generic"}
+STEP_KERNELS = {5: "stream", 6: "stream-barrier", 7: "stream-3xtf32", 3: "dual", 0: "generic"}
 
 
 @pytest.fixture
