@@ -316,6 +316,173 @@ __global__ void __launch_bounds__(NTHREADS, 2) step_kernel(const StepArgs a) {
 }
 
 
+// ---- N4 fast path: the encoder launch of an inference rollout fed by trial descriptors.
+// With I0 in {0, 1} on the seeds, S0 = 1 - I0, R0 = 0 (ode_nn_ngraph_sim.py:371-390) every row of the batch is one of TWO
+// kinds, so encoder, I'_0 = sigmoid(W enc + b) and the decoder of grid point 0 are evaluated for those two rows only --
+// by the SAME device functions the generic encoder launch runs per row (GN_ENC arithmetic, gemm_sigmoid[_tc] on a tile
+// whose rows 0 / 1 are enc(0) / enc(1), decode_row), so the result is bitwise the dense path's -- and kept in a small
+// table (trials_table_kernel, one CTA). The encoder launch itself becomes a stream of stores (fill_trials_kernel: every row
+// as a susceptible row; seed_rows_kernel: the seed rows patched afterwards, O(rows + seeds)): S0, I0, I'_0 rows,
+// beta / gamma, hid(I_0), hid(R_0), probs[0]; no dense x block is expanded or read.
+// table layout (floats): kind k in {0 = susceptible, 1 = seed}
+constexpr int TB_E = 0;        // enc(0)[64], enc(1)[64]
+constexpr int TB_IP = 128;     // I'_0 of kind k [64] at TB_IP + 64 k
+constexpr int TB_PR = 256;     // probs[0] of kind k [4] at TB_PR + 4 k
+constexpr int TB_HI = 264;     // hid(I_0) of kind k [4] at TB_HI + 4 k
+constexpr int TB_HR = 272;     // hid(R_0) [4]
+constexpr int TB_FLOATS = 276;
+
+template <int VAR>
+__global__ void __launch_bounds__(NTHREADS, 1) trials_table_kernel(const gnode_params_t p, float* __restrict__ tbl_g) {
+    constexpr bool TC = (VAR & VAR_TC) != 0;
+    constexpr bool FAST = (VAR & VAR_FASTSIG) != 0;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Xs = smem + SM_X;
+    unsigned char* SPs = smem + SM_SP;
+    float* Ws = reinterpret_cast<float*>(smem + SM_W);
+    float* bs = reinterpret_cast<float*>(smem + SM_B);
+    float* W3s = reinterpret_cast<float*>(smem + SM_W3);
+    float* w1s = reinterpret_cast<float*>(smem + SM_W1);
+    float* b1s = reinterpret_cast<float*>(smem + SM_B1);
+    float* small = reinterpret_cast<float*>(smem + SM_SMALL);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SM_MBAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + SM_MBAR + 8);
+    const int tid = threadIdx.x, l = tid & 15, hw = tid >> 4;
+
+    umma::Ctx cx;
+    if (TC) {
+        umma::prepare_weights(p.lin_w, smem + SM_W, smem + SM_WLO, tid, NTHREADS);
+        if (tid < 32) umma::tmem_alloc(tslot, umma::TMEM_COLS);
+        if (tid == 0) umma::mbar_init(mbar, 1);
+        umma::fence_before_sync();
+    } else {
+        for (int i = tid; i < H * H / 4; i += NTHREADS)
+            reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(p.lin_w)[i];
+    }
+    if (tid < H) { bs[tid] = p.lin_b[tid]; w1s[tid] = p.s1_w[tid]; b1s[tid] = p.s1_b[tid]; }
+    if (tid < 4 * H) W3s[tid] = p.l3_w[tid];
+    if (tid < 4) { small[tid] = p.l3_b[tid]; small[4 + tid] = p.s2_w[tid]; }
+    if (tid == 0) small[8] = p.s2_b[0];
+    __syncthreads();
+    if (TC) {
+        umma::fence_after_sync();
+        cx.tmem = *tslot; cx.bar = mbar; cx.phase = 0;
+        cx.whi = umma::smem_u32(smem + SM_W); cx.wlo = umma::smem_u32(smem + SM_WLO);
+    }
+    // the two encoded vectors (this lane's 4 channels): e0 = enc(0), e1 = enc(1), op for op the generic encoder's
+    // relu(c * w1 + b1) with explicit _rn ops
+    float4 e0, e1;
+    {
+        const float4 w = *reinterpret_cast<const float4*>(w1s + 4 * l);
+        const float4 b = *reinterpret_cast<const float4*>(b1s + 4 * l);
+#define GN_ENC2(c)                                                      \
+    e0.c = fmaxf(__fadd_rn(__fmul_rn(0.f, w.c), b.c), 0.f);             \
+    e1.c = fmaxf(__fadd_rn(__fmul_rn(1.f, w.c), b.c), 0.f);
+        GN_ENC2(x) GN_ENC2(y) GN_ENC2(z) GN_ENC2(w)
+#undef GN_ENC2
+    }
+    // operand tile: row 0 = enc(I0 = 0), row 1 = enc(I0 = 1), the other rows zero
+    for (int idx = tid; idx < TILE * CHUNKS; idx += NTHREADS) {
+        const int rr = idx >> 4;
+        sts4(Xs, sw_off(rr, idx & 15), rr == 0 ? e0 : (rr == 1 ? e1 : make_float4(0.f, 0.f, 0.f, 0.f)));
+    }
+    // decoder of the two kinds of rows (half-warps 0 and 1: both halves of warp 0 take part in the shuffles)
+    if (tid < 32) {
+        const bool seed = hw == 1;                           // row (S0, I0, R0) = seed ? (0, 1, 0) : (1, 0, 0)
+        decode_row(seed ? e0 : e1, seed ? e1 : e0, e0, W3s, small, l, true, tbl_g + TB_PR + 4 * hw, tbl_g + TB_HI + 4 * hw,
+                   seed ? nullptr : tbl_g + TB_HR);
+        if (tid < 16) {
+            *reinterpret_cast<float4*>(tbl_g + TB_E + 4 * l) = e0;
+            *reinterpret_cast<float4*>(tbl_g + TB_E + 64 + 4 * l) = e1;
+        }
+    }
+    __syncthreads();
+    if (TC) umma::gemm_sigmoid_tc<FAST>(cx, Xs, SPs, bs, tid);
+    else gemm_sigmoid<FAST>(Xs, Ws, bs, SPs, tid);
+    __syncthreads();
+    if (tid < 32) *reinterpret_cast<float4*>(tbl_g + TB_IP + 64 * hw + 4 * l) = lds4(SPs, sw_off(hw, l));
+    if (TC) {
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid < 32) umma::tmem_dealloc(cx.tmem, umma::TMEM_COLS);
+    }
+}
+
+// every row of the batch written as a susceptible row (a warp per 32 consecutive rows: the three 256-byte rows by
+// half-warps, then one thread per row for the scalars)
+__global__ void __launch_bounds__(256) fill_trials_kernel(const StepArgs a, const float* __restrict__ tbl,
+                                                          const float* __restrict__ beta_i, const float* __restrict__ gamma_i) {
+    const int lane = threadIdx.x & 31, l = lane & 15, h = lane >> 4;
+    const int M = a.bv.M;
+    const size_t plane = (size_t)M * H;
+    const float4 s0 = *reinterpret_cast<const float4*>(tbl + TB_E + 64 + 4 * l);     // S0 = 1
+    const float4 i0 = *reinterpret_cast<const float4*>(tbl + TB_E + 4 * l);          // I0 = 0
+    const float4 ip = *reinterpret_cast<const float4*>(tbl + TB_IP + 4 * l);
+    const float4 hi = *reinterpret_cast<const float4*>(tbl + TB_HI), hr = *reinterpret_cast<const float4*>(tbl + TB_HR);
+    const float4 pr = *reinterpret_cast<const float4*>(tbl + TB_PR);
+    const int64_t n_groups = ((int64_t)M + 31) / 32;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t grp = warp0; grp < n_groups; grp += n_warps) {
+        const int64_t g0 = grp * 32;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const int64_t g = g0 + 2 * j + h;
+            if (g < M) {
+                const size_t off = (size_t)g * H + 4 * l;
+                stg4_stream(a.y_out + off, s0);
+                stg4_stream(a.y_out + plane + off, i0);
+                stg4_stream(a.ip_out + off, ip);
+            }
+        }
+        const int64_t g = g0 + lane;
+        if (g < M) {
+            const int inst = find_instance(a.bv, g);
+            a.beta[g] = beta_i[inst]; a.gamma[g] = gamma_i[inst];
+            *reinterpret_cast<float4*>(a.hid_i + (size_t)g * 4) = hi;
+            *reinterpret_cast<float4*>(a.hid_r + (size_t)g * 4) = hr;
+            if (a.probs != nullptr) {
+                float* out = a.probs + (size_t)g * 3;
+                out[0] = pr.x; out[1] = pr.y; out[2] = pr.z;
+            }
+        }
+    }
+}
+
+// the seed rows (I0 = 1, S0 = 0): a half-warp per seed entry; entries out of range are ignored (as gnode_expand_trials)
+__global__ void __launch_bounds__(256) seed_rows_kernel(const StepArgs a, const float* __restrict__ tbl,
+                                                        const int32_t* __restrict__ seeds, const int32_t* __restrict__ seed_ptr) {
+    const int l = threadIdx.x & 15;
+    const int total = seed_ptr[a.bv.n_inst];
+    const size_t plane = (size_t)a.bv.M * H;
+    const float4 s0 = *reinterpret_cast<const float4*>(tbl + TB_E + 4 * l);          // S0 = 0
+    const float4 i0 = *reinterpret_cast<const float4*>(tbl + TB_E + 64 + 4 * l);     // I0 = 1
+    const float4 ip = *reinterpret_cast<const float4*>(tbl + TB_IP + 64 + 4 * l);
+    const int hw0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, n_hw = (gridDim.x * blockDim.x) >> 4;
+    for (int e = hw0; e < total; e += n_hw) {
+        int lo = 0, hi = a.bv.n_inst - 1;                    // instance that owns seed entry e
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seed_ptr[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const GnInstance I = a.bv.inst[lo];
+        const int s = seeds[e];
+        if (s < 0 || s >= I.n) continue;
+        const int64_t g = I.row0 + s;
+        const size_t off = (size_t)g * H + 4 * l;
+        stg4_stream(a.y_out + off, s0);
+        stg4_stream(a.y_out + plane + off, i0);
+        stg4_stream(a.ip_out + off, ip);
+        if (l == 0) {
+            *reinterpret_cast<float4*>(a.hid_i + (size_t)g * 4) = *reinterpret_cast<const float4*>(tbl + TB_HI + 4);
+            if (a.probs != nullptr) {
+                float* out = a.probs + (size_t)g * 3;
+                out[0] = tbl[TB_PR + 4]; out[1] = tbl[TB_PR + 5]; out[2] = tbl[TB_PR + 6];
+            }
+        }
+    }
+}
+
 // small device helpers of the pipelined step kernels
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -1263,9 +1430,62 @@ int make_out_sel(int T, const int32_t* out_steps, int32_t n_out, OutSel* o, cons
     return GNODE_OK;
 }
 
+// trial descriptors of a descriptor-fed inference rollout (gnode_rollout_forward_trials) and 2 KB of device scratch
+struct TrialDesc {
+    const int32_t* seeds; const int32_t* seed_ptr;
+    const float* beta; const float* gamma;
+    float* table;
+};
+
+// GNODE_TRIALS_ENCODE=dense keeps the expansion into the dense block + the generic encoder launch (A/B, read once)
+static bool trials_fast_enabled() {
+    static const bool on = !(getenv("GNODE_TRIALS_ENCODE") && !strcmp(getenv("GNODE_TRIALS_ENCODE"), "dense"));
+    return on;
+}
+// the descriptor-fed encoder writes no R plane and no trajectory: inference with R carried as hid(R) only
+static bool trials_fast_applies(const float* traj, int32_t T) {
+    return trials_fast_enabled() && use_dual() && !traj && T > 1 && r_state_choice() == 1;
+}
+
+// head of the trials workspace: the dense [M][GNODE_TRIAL_LDX] block of the expansion path, or the two-row table
+static size_t trials_block_bytes(const gnode_batch* b) {
+    return align_up(std::max((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), (size_t)TB_FLOATS * sizeof(float)), 256);
+}
+
+template <int VAR>
+static int launch_trials_table(const gnode_batch* b, const gnode_params_t& p, float* table, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(trials_table_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        configured[b->device & 63] = true;
+    }
+    trials_table_kernel<VAR><<<1, NTHREADS, SM_TOTAL, stream>>>(p, table);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
+static int launch_encode_trials(const gnode_batch* b, const StepArgs& a, const TrialDesc& td, cudaStream_t stream) {
+    int rc;
+    switch (current_variant()) {
+        case 0: rc = launch_trials_table<0>(b, a.p, td.table, stream); break;
+        case 1: rc = launch_trials_table<1>(b, a.p, td.table, stream); break;
+        case 2: rc = launch_trials_table<2>(b, a.p, td.table, stream); break;
+        default: rc = launch_trials_table<3>(b, a.p, td.table, stream); break;
+    }
+    if (rc) return rc;
+    const int64_t groups = ((int64_t)b->M + 31) / 32;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((groups + 7) / 8, (int64_t)b->sm_count * 8));
+    fill_trials_kernel<<<grid, 256, 0, stream>>>(a, td.table, td.beta, td.gamma);
+    GN_LAUNCH_CHECK();
+    seed_rows_kernel<<<std::max(1, std::min(b->n_inst, b->sm_count * 8)), 256, 0, stream>>>(a, td.table, td.seeds, td.seed_ptr);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
 static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, const gnode_params_t* p, int32_t T,
                                 const float* dt_host, const OutSel& sel, float* traj, float* aux, int32_t* aux_filled,
-                                float* probs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                float* probs, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                                const TrialDesc* td = nullptr) {
     if (aux_filled) *aux_filled = 0;
     if (workspace_bytes < gnode_rollout_workspace_bytes(b, traj != nullptr)) {
         set_error("gnode_rollout_forward: workspace too small (%zu < %zu)", workspace_bytes,
@@ -1338,7 +1558,11 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     a.hid_i = dual ? hid_i : nullptr;
     const bool rfree = dual && !traj && T > 1 && r_state_choice() == 1;
     a.hid_r = rfree ? hid_r : nullptr;
-    rc = launch_step<MODE_ENCODE>(b, a, stream);      // y_0, I'_0, probs[0] (+ hid(I_0))
+    if (td) {                                         // descriptor-fed: two kinds of rows, a stream of stores
+        if (!rfree) { set_error("gnode_rollout_forward_trials: internal: descriptor encoder without hid(R) state"); return GNODE_ERR_ARG; }
+        rc = launch_encode_trials(b, a, *td, stream);
+    } else
+        rc = launch_step<MODE_ENCODE>(b, a, stream);  // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
     a.n_steps = 0; a.k0 = 0;
     // Persistent rollout: ONE cooperative launch runs all T-1 Euler steps with a grid barrier between them (no per-step
@@ -1502,7 +1726,7 @@ extern "C" int gnode_expand_trials(gnode_batch_t b, const int32_t* seeds, const 
 
 extern "C" size_t gnode_rollout_trials_workspace_bytes(gnode_batch_t b, int with_traj) {
     if (!b) return 0;
-    return gnode_rollout_workspace_bytes(b, with_traj) + align_up((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), 256);
+    return gnode_rollout_workspace_bytes(b, with_traj) + gnode::trials_block_bytes(b);
 }
 
 extern "C" int gnode_rollout_forward_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr,
@@ -1513,8 +1737,21 @@ extern "C" int gnode_rollout_forward_trials(gnode_batch_t b, const int32_t* seed
         set_error("gnode_rollout_forward_trials: workspace missing or too small");
         return GNODE_ERR_ARG;
     }
-    const size_t xbytes = align_up((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), 256);
+    const size_t xbytes = gnode::trials_block_bytes(b);
     float* x = (float*)workspace;
+    if (gnode::trials_fast_applies(traj, T)) {
+        // every row is one of two kinds: no dense block, the encoder launch is a stream of stores (trials_table_kernel)
+        if (!seeds || !seed_ptr || !beta || !gamma || !p || !probs || T < 1 || !dt_host) {
+            set_error("gnode_rollout_forward_trials: bad arguments (T=%d)", T);
+            return GNODE_ERR_ARG;
+        }
+        gnode::OutSel sel;
+        int rc = gnode::make_out_sel(T, out_steps, n_out, &sel, "gnode_rollout_forward_trials");
+        if (rc) return rc;
+        const gnode::TrialDesc td{seeds, seed_ptr, beta, gamma, x};      // the table lives where the dense block would
+        return gnode::rollout_forward_impl(b, nullptr, 0, p, T, dt_host, sel, traj, nullptr, nullptr, probs,
+                                           (unsigned char*)workspace + xbytes, workspace_bytes - xbytes, (cudaStream_t)stream_, &td);
+    }
     int rc = gnode_expand_trials(b, seeds, seed_ptr, beta, gamma, x, GNODE_TRIAL_LDX, stream_);
     if (rc) return rc;
     return gnode_rollout_forward_sel(b, x, GNODE_TRIAL_LDX, p, T, dt_host, out_steps, n_out, traj, probs,
