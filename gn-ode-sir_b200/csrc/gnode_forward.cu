@@ -69,6 +69,11 @@ struct StepArgs {
     float* aux;           // persistent rollout: base of the buffer, or null
     int64_t aux_slot;     // floats per grid point = 2 (Mr + 1) H
     int ip_zrow;          // row index of the all-zero row of an I' plane (M for the ping-pong buffers)
+    // Euler step 0 of a descriptor-fed inference rollout fused with the encoder (step_stream_kernel, OPT bit 7)
+    const float* z_tbl;          // two-row table of trials_table_kernel
+    const uint32_t* z_bitmap;    // bit g = row g is a seed row
+    const float* z_beta;         // [n_inst]
+    const float* z_gamma;        // [n_inst]
     alignas(64) CUtensorMap tm_ip_out;   // [M rows][64] fp32 over ip_out, box 32 x 128, SWIZZLE_128B
     alignas(64) CUtensorMap tm_ipb[2];   // the same over ipb[0] / ipb[1] (persistent rollout)
     // step_stream_kernel: the S_k tile arrives by TMA tensor loads (same box / swizzle = the UMMA operand layout)
@@ -480,6 +485,24 @@ __global__ void __launch_bounds__(256) seed_rows_kernel(const StepArgs a, const 
                 out[0] = tbl[TB_PR + 4]; out[1] = tbl[TB_PR + 5]; out[2] = tbl[TB_PR + 6];
             }
         }
+    }
+}
+
+// bit g of the bitmap = global row g is a seed row (the bitmap is zeroed before); entries out of range are ignored
+__global__ void __launch_bounds__(256) seed_bitmap_kernel(const GnBatchView bv, const int32_t* __restrict__ seeds,
+                                                          const int32_t* __restrict__ seed_ptr, uint32_t* __restrict__ bitmap) {
+    const int total = seed_ptr[bv.n_inst];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int lo = 0, hi = bv.n_inst - 1;                      // instance that owns seed entry e
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seed_ptr[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const GnInstance I = bv.inst[lo];
+        const int s = seeds[e];
+        if (s < 0 || s >= I.n) continue;
+        const int64_t g = (int64_t)I.row0 + s;
+        atomicOr(&bitmap[g >> 5], 1u << (g & 31));
     }
 }
 
@@ -1230,6 +1253,20 @@ static int launch_step_stream(const gnode_batch* b, const StepArgs& a, cudaStrea
     return GNODE_OK;
 }
 
+// Euler step 0 of a descriptor-fed inference rollout, fused with the encoder (OPT bit 7 of step_stream_kernel)
+template <bool FAST, int OPT>
+static int launch_step_stream_zero(const gnode_batch* b, const StepArgs& a, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    if (!configured[b->device & 63]) {
+        GN_CUDA(cudaFuncSetAttribute(step_stream_kernel<FAST, false, true, OPT | 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::TOTAL));
+        configured[b->device & 63] = true;
+    }
+    const int grid = std::min(b->n_tiles, b->sm_count);
+    step_stream_kernel<FAST, false, true, OPT | 128><<<grid, D_THREADS, StreamCfg::TOTAL, stream>>>(a);
+    GN_LAUNCH_CHECK();
+    return GNODE_OK;
+}
+
 // 5 = pipelined kernel with the TMA-fed S stream (default), 6 = 5 without the deferred store wait, 7 = 5 with 3xTF32 (the
 // lo x lo term of the 4-term split product dropped: +2 % speed, per-product error 2^-21 + 2^-21 instead of 2^-21 + 2^-22;
 // still inside the 1e-5 bar on every golden, tools/kernel_error_table.py), 3 = the same pipeline with LDG-fed operands
@@ -1434,14 +1471,21 @@ int make_out_sel(int T, const int32_t* out_steps, int32_t n_out, OutSel* o, cons
 struct TrialDesc {
     const int32_t* seeds; const int32_t* seed_ptr;
     const float* beta; const float* gamma;
-    float* table;
+    float* table;          // TB_FLOATS floats
+    uint32_t* bitmap;      // one bit per row of the batch (fused step 0)
 };
+constexpr size_t TRIALS_TABLE_BYTES = 4096;
 
-// GNODE_TRIALS_ENCODE=dense keeps the expansion into the dense block + the generic encoder launch (A/B, read once)
-static bool trials_fast_enabled() {
-    static const bool on = !(getenv("GNODE_TRIALS_ENCODE") && !strcmp(getenv("GNODE_TRIALS_ENCODE"), "dense"));
-    return on;
+// GNODE_TRIALS_ENCODE (A/B, read once): "dense" keeps the expansion into the dense block + the generic encoder launch,
+// "fill" the descriptor-fed encoder launch without fusing Euler step 0 into it; default: both
+static int trials_encode_mode() {
+    static const int mode = [] {
+        const char* e = getenv("GNODE_TRIALS_ENCODE");
+        return !e ? 2 : !strcmp(e, "dense") ? 0 : !strcmp(e, "fill") ? 1 : 2;
+    }();
+    return mode;
 }
+static bool trials_fast_enabled() { return trials_encode_mode() != 0; }
 // the descriptor-fed encoder writes no R plane and no trajectory: inference with R carried as hid(R) only
 static bool trials_fast_applies(const float* traj, int32_t T) {
     return trials_fast_enabled() && use_dual() && !traj && T > 1 && r_state_choice() == 1;
@@ -1449,7 +1493,8 @@ static bool trials_fast_applies(const float* traj, int32_t T) {
 
 // head of the trials workspace: the dense [M][GNODE_TRIAL_LDX] block of the expansion path, or the two-row table
 static size_t trials_block_bytes(const gnode_batch* b) {
-    return align_up(std::max((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), (size_t)TB_FLOATS * sizeof(float)), 256);
+    static_assert(TB_FLOATS * sizeof(float) <= TRIALS_TABLE_BYTES, "table");
+    return align_up(std::max((size_t)b->M * GNODE_TRIAL_LDX * sizeof(float), TRIALS_TABLE_BYTES + ((size_t)b->M + 31) / 32 * 4), 256);
 }
 
 template <int VAR>
@@ -1464,15 +1509,16 @@ static int launch_trials_table(const gnode_batch* b, const gnode_params_t& p, fl
     return GNODE_OK;
 }
 
-static int launch_encode_trials(const gnode_batch* b, const StepArgs& a, const TrialDesc& td, cudaStream_t stream) {
-    int rc;
+static int launch_trials_table_v(const gnode_batch* b, const gnode_params_t& p, float* table, cudaStream_t stream) {
     switch (current_variant()) {
-        case 0: rc = launch_trials_table<0>(b, a.p, td.table, stream); break;
-        case 1: rc = launch_trials_table<1>(b, a.p, td.table, stream); break;
-        case 2: rc = launch_trials_table<2>(b, a.p, td.table, stream); break;
-        default: rc = launch_trials_table<3>(b, a.p, td.table, stream); break;
+        case 0: return launch_trials_table<0>(b, p, table, stream);
+        case 1: return launch_trials_table<1>(b, p, table, stream);
+        case 2: return launch_trials_table<2>(b, p, table, stream);
+        default: return launch_trials_table<3>(b, p, table, stream);
     }
-    if (rc) return rc;
+}
+
+static int launch_encode_trials(const gnode_batch* b, const StepArgs& a, const TrialDesc& td, cudaStream_t stream) {
     const int64_t groups = ((int64_t)b->M + 31) / 32;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((groups + 7) / 8, (int64_t)b->sm_count * 8));
     fill_trials_kernel<<<grid, 256, 0, stream>>>(a, td.table, td.beta, td.gamma);
@@ -1558,9 +1604,36 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     a.hid_i = dual ? hid_i : nullptr;
     const bool rfree = dual && !traj && T > 1 && r_state_choice() == 1;
     a.hid_r = rfree ? hid_r : nullptr;
-    if (td) {                                         // descriptor-fed: two kinds of rows, a stream of stores
+    // Persistent rollout: ONE cooperative launch runs all T-1 Euler steps (see below); decided here because the
+    // descriptor-fed encoder fuses Euler step 0 only into the launch-per-step form
+    const int persistent_mode = persistent_choice();
+    const bool persistent_ok = persistent_mode < 0 ? b->n_tiles <= 32 * b->sm_count : persistent_mode != 0;
+    int coop = 0;
+    if (dual && persistent_ok && T > 2 && T - 1 <= 1023 && !(a.dbg & 64) && (!aux_on || (size_t)T * 2 * Ms < ((size_t)1 << 31)))
+        GN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device));
+    bool step0_fused = false;
+    if (td) {                                         // descriptor-fed: two kinds of rows
         if (!rfree) { set_error("gnode_rollout_forward_trials: internal: descriptor encoder without hid(R) state"); return GNODE_ERR_ARG; }
-        rc = launch_encode_trials(b, a, *td, stream);
+        rc = launch_trials_table_v(b, a.p, td->table, stream);
+        if (rc) return rc;
+        const int sk = step_kernel_choice();
+        step0_fused = trials_encode_mode() == 2 && !coop && stream_kernel && have_tma && (sk == 5 || sk == 7);
+        if (step0_fused) {
+            // encoder + Euler step 0 in one launch: y_0 and I'_0 are never written (step_stream_kernel, OPT bit 7)
+            GN_CUDA(cudaMemsetAsync(td->bitmap, 0, (M + 31) / 32 * 4, stream));
+            seed_bitmap_kernel<<<std::max(1, std::min(b->n_inst, b->sm_count * 8)), 256, 0, stream>>>(a.bv, td->seeds, td->seed_ptr, td->bitmap);
+            GN_LAUNCH_CHECK();
+            a.z_tbl = td->table; a.z_bitmap = td->bitmap; a.z_beta = td->beta; a.z_gamma = td->gamma;
+            a.y_in = nullptr; a.ip_in = nullptr; a.y_out = state(1); a.ip_out = ipk(1);
+            a.use_tma = 2; a.tm_ip_out = tm_ip[1];
+            a.probs = out(0); a.dt = dt_host[0];
+            a.n_steps = 0; a.k0 = 0;
+            a.counter = (a.dbg & 64) ? nullptr : counters + 1;
+            const bool fast = (current_variant() & VAR_FASTSIG) != 0;
+            rc = sk == 7 ? (fast ? launch_step_stream_zero<true, 97>(b, a, stream) : launch_step_stream_zero<false, 97>(b, a, stream))
+                         : (fast ? launch_step_stream_zero<true, 65>(b, a, stream) : launch_step_stream_zero<false, 65>(b, a, stream));
+        } else
+            rc = launch_encode_trials(b, a, *td, stream);   // a stream of stores: y_0, I'_0, probs[0], hid(I_0), hid(R_0)
     } else
         rc = launch_step<MODE_ENCODE>(b, a, stream);  // y_0, I'_0, probs[0] (+ hid(I_0))
     if (rc) return rc;
@@ -1570,11 +1643,6 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     // Default: batches of up to 16 tiles per pipeline (~600k rows), where a launch per step costs >= 2 % ; larger batches
     // keep one launch per step (the persistent variant reads its per-step operands from shared memory: -1 % there).
     // gnode_set_persistent / GNODE_PERSISTENT=1 / 0 forces it on / off.
-    const int persistent_mode = persistent_choice();
-    const bool persistent_ok = persistent_mode < 0 ? b->n_tiles <= 32 * b->sm_count : persistent_mode != 0;
-    int coop = 0;
-    if (dual && persistent_ok && T > 2 && T - 1 <= 1023 && !(a.dbg & 64) && (!aux_on || (size_t)T * 2 * Ms < ((size_t)1 << 31)))
-        GN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device));
     if (coop) {
         // step sizes / output slots: carried in the kernel parameters when the grid is uniform and the selection an
         // arithmetic progression (the reference's np.arange grid and int(i/deltaT) selection); otherwise copied to the
@@ -1614,7 +1682,7 @@ static int rollout_forward_impl(gnode_batch_t b, const float* x, int64_t ldx, co
     }
     a.aux = nullptr;
     if (!coop)
-    for (int k = 0; k + 1 < T; ++k) {
+    for (int k = step0_fused ? 1 : 0; k + 1 < T; ++k) {
         a.y_in = state(k); a.y_out = state(k + 1);
         a.ip_in = ipk(k); a.ip_out = ipk(k + 1);
         a.ai_out = aux_on ? ipk(k) + Ms * H : nullptr;
@@ -1748,7 +1816,8 @@ extern "C" int gnode_rollout_forward_trials(gnode_batch_t b, const int32_t* seed
         gnode::OutSel sel;
         int rc = gnode::make_out_sel(T, out_steps, n_out, &sel, "gnode_rollout_forward_trials");
         if (rc) return rc;
-        const gnode::TrialDesc td{seeds, seed_ptr, beta, gamma, x};      // the table lives where the dense block would
+        // the table and the seed bitmap live where the dense block would
+        const gnode::TrialDesc td{seeds, seed_ptr, beta, gamma, x, (uint32_t*)((unsigned char*)workspace + gnode::TRIALS_TABLE_BYTES)};
         return gnode::rollout_forward_impl(b, nullptr, 0, p, T, dt_host, sel, traj, nullptr, nullptr, probs,
                                            (unsigned char*)workspace + xbytes, workspace_bytes - xbytes, (cudaStream_t)stream_, &td);
     }

@@ -49,6 +49,8 @@ struct StreamCfg {
     static constexpr int P_HR = P_HS + TR * 16;            // hid(R_k) / W3 I'_k [TR][4]
     static constexpr int P_CI = P_HR + TR * 16;            // colidx slice + 64 B over-read pad
     static constexpr int P_PM = P_CI + CAP * 4 + 64;       // work items of the gather: [64] x {a, b | c, d} tile rows (256 B)
+    static constexpr int P_ZK = P_PM;                      // step 0 from descriptors (no work items, no staged colidx slice):
+    static constexpr int P_ZI = P_CI;                      // seed flag [TR] and instance [TR] of every tile row
     static constexpr int P_BYTES = ((P_PM + 256 + 1023) / 1024) * 1024;
     static constexpr int TOTAL = D_SHARED + 2 * P_BYTES + 1024;
     static constexpr int TMEM_COLS = 512;                 // two [128 x 160] fp32 accumulators, 256 columns apart
@@ -161,9 +163,17 @@ struct SStep {
     float dt;
 };
 
-template <bool FAST, bool PERSIST, bool RF, int OPT>      // OPT bit 0: no block barrier after the I' store (see P5)
+// OPT bit 0: no block barrier after the I' store (see P5); bit 7 (ZS): Euler step 0 of a descriptor-fed inference rollout
+// fused with the encoder. There y_0 has two kinds of rows (seed: I0 = 1, S0 = 0; susceptible: S0 = 1, I0 = 0;
+// ode_nn_ngraph_sim.py:371-390), so nothing is read but the CSR, a seed bitmap and the two-row table of
+// trials_table_kernel: the S_0 tile is synthesised in shared memory, the neighbour sum is the same sequence of additions
+// over the two possible I'_0 rows (bitwise the gather of the encoder's I'_0 plane), I_0 / I'_0 / hid(R_0) / probs[0] come
+// from the table. Neither y_0 nor I'_0 is ever written: the launch stores y_1, I'_1, hid(I_1), hid(R_1), beta / gamma.
+template <bool FAST, bool PERSIST, bool RF, int OPT>
 __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_constant__ StepArgs a) {
     using C = StreamCfg;
+    constexpr bool ZS = (OPT & 128) != 0;
+    static_assert(!ZS || (RF && !PERSIST && (OPT & 64)), "step 0 from descriptors: inference without an R plane, one launch, raw S tile");
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -190,6 +200,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     int* ci_s = reinterpret_cast<int*>(hb + C::P_CI);
     unsigned* hub_mask = reinterpret_cast<unsigned*>(rp_s + TR + 2);
     const uint32_t* items_s = reinterpret_cast<const uint32_t*>(hb + C::P_PM);
+    unsigned char* kind_s = hb + C::P_ZK;                             // ZS: 1 = seed row
+    int* zinst_s = reinterpret_cast<int*>(hb + C::P_ZI);              // ZS: instance of every tile row
     const int bar_id = 1 + half;
 #define HSYNC() umma::bar_sync(bar_id, PT)
 
@@ -229,6 +241,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     };
     // the same thread: request the S_k rows of that tile (raw fp32, operand layout) into Xs
     auto issue_s_load = [&]() {
+        if (ZS) {                                                     // nothing to load: P1 synthesises the S_0 rows
+            if (meta->seq < n_tiles) umma::mbar_arrive(sbar);
+            return;
+        }
         if (meta->seq < n_tiles) {
             mbar_expect_tx(sbar, 2 * C::KBLK);
             const int r0 = STP_SROW0() + meta->tile0;
@@ -267,6 +283,15 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     const int n_steps = PERSIST ? max(a.n_steps, 1) : 1;
 
     const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
+    // ZS: this lane's 16-byte chunk of enc(0), enc(1) and of the two I'_0 rows (trials_table_kernel)
+    float4 ze0 = make_float4(0.f, 0.f, 0.f, 0.f), ze1 = ze0, zip0 = ze0, zip1 = ze0;
+    if (ZS) {
+        ze0 = *reinterpret_cast<const float4*>(a.z_tbl + TB_E + 4 * l);
+        ze1 = *reinterpret_cast<const float4*>(a.z_tbl + TB_E + 64 + 4 * l);
+        zip0 = *reinterpret_cast<const float4*>(a.z_tbl + TB_IP + 4 * l);
+        zip1 = *reinterpret_cast<const float4*>(a.z_tbl + TB_IP + 64 + 4 * l);
+    }
+    auto seed_bit = [&](int64_t g) -> int { return (int)((a.z_bitmap[g >> 5] >> (g & 31)) & 1u); };
 
 #pragma unroll 1
     for (int step = 0; step < n_steps; ++step) {
@@ -321,18 +346,37 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             int rpv = 0, civ[3] = {0, 0, 0};
             float bgv = 0.f;
             uint32_t pmv = 0;
-            if (single && t < 64) pmv = __ldg(reinterpret_cast<const uint32_t*>(a.bv.tile_perm) + (size_t)(tile0 / TR) * 64 + t);
+            if (!ZS && single && t < 64) pmv = __ldg(reinterpret_cast<const uint32_t*>(a.bv.tile_perm) + (size_t)(tile0 / TR) * 64 + t);
             const int ecnt = min(m.ecnt, C::CAP);
             if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
-            if (single) {
+            if (!ZS && single) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) civ[u] = __ldg(m.colidx + ebase + t + u * PT);
             }
-            if (t >= PT / 2 && t < PT / 2 + nrows) bgv = a.beta[tile0 + t - PT / 2];
-            if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
-            umma::mbar_wait(sbar, sphase); sphase ^= 1;               // the S_k tile has landed in Xs
+            if (!ZS && t >= PT / 2 && t < PT / 2 + nrows) bgv = a.beta[tile0 + t - PT / 2];
+            if (!ZS && t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bgv = a.gamma[tile0 + t - 3 * PT / 4];
+            int zi = m.inst0, zk = 0;
+            float zg = 0.f;
+            if (ZS && t < nrows) {                                    // row t: instance, seed flag, beta / gamma of its trial
+                if (!single) zi = find_instance(a.bv, (int64_t)tile0 + t);
+                zk = seed_bit((int64_t)tile0 + t);
+                bgv = a.z_beta[zi]; zg = a.z_gamma[zi];
+                a.beta[tile0 + t] = bgv; a.gamma[tile0 + t] = zg;
+            }
+            umma::mbar_wait(sbar, sphase); sphase ^= 1;               // the S_k tile has landed in Xs (ZS: Xs and Ls are free)
+            if (ZS) {
 #pragma unroll
-            for (int i = 0; i < ((OPT & 8) ? 0 : 4); ++i) {
+                for (int i = 0; i < 4; ++i) {                         // S_0 rows: enc(1 - I0), raw = hi operand; lo as below
+                    const int rr = hw + i * RSTEP;
+                    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);      // rows past M: zeros, as the TMA load delivers them
+                    if (rr < nrows) s0 = seed_bit((int64_t)tile0 + rr) ? ze0 : ze1;
+                    sts4(Xs, off0 + i * PASS, s0);
+                    sts4(Ls, off0 + i * PASS, umma::tf32_trunc_lo4(s0));
+                }
+                if (t < nrows) { kind_s[t] = (unsigned char)zk; zinst_s[t] = zi; bg_s[t] = bgv; bg_s[TR + t] = zg; }
+            }
+#pragma unroll
+            for (int i = 0; i < ((OPT & 8) || ZS ? 0 : 4); ++i) {
                 if (OPT & 64) { sts4(Ls, off0 + i * PASS, umma::tf32_trunc_lo4(lds4(Xs, off0 + i * PASS))); continue; }
                 float4 lo;
                 const float4 pk = tf32_pack4(lds4(Xs, off0 + i * PASS), lo);
@@ -343,13 +387,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (t == 0) *row_ctr = 0;
             if (t < TR / 32) hub_mask[t] = 0u;
             if (single && t <= nrows) rp_s[t] = rpv;
-            if (single && t < 64) reinterpret_cast<uint32_t*>(hb + C::P_PM)[t] = pmv;
-            if (single) {
+            if (!ZS && single && t < 64) reinterpret_cast<uint32_t*>(hb + C::P_PM)[t] = pmv;
+            if (!ZS && single) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = civ[u];   // instance-local ids
             }
-            if (t >= PT / 2 && t < PT / 2 + nrows) bg_s[t - PT / 2] = bgv;
-            if (t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bg_s[TR + t - 3 * PT / 4] = bgv;
+            if (!ZS && t >= PT / 2 && t < PT / 2 + nrows) bg_s[t - PT / 2] = bgv;
+            if (!ZS && t >= 3 * PT / 4 && t < 3 * PT / 4 + nrows) bg_s[TR + t - 3 * PT / 4] = bgv;
         }
         HSYNC();                                                                // S1
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
@@ -470,7 +514,41 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         };
 
         // ---- P3a: neighbour sums AI (sequential, ascending columns), folded into S' in place
-        {
+        if (ZS) {
+            // step 0 from descriptors: neighbour c contributes I'_0(seed) or I'_0(susceptible) -- the same additions in the
+            // same order as the gather of an I'_0 plane, with a bitmap bit per neighbour instead of a 256-byte row
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                const int rr = hw + RSTEP * it;
+                int deg = 0, row0 = i_row0;
+                const int32_t* cp = nullptr;
+                if (rr < nrows) {
+                    if (single) {
+                        deg = rp_s[rr + 1] - rp_s[rr];
+                        cp = m.colidx + rp_s[rr];
+                    } else {
+                        const GnInstance I = a.bv.inst[zinst_s[rr]];
+                        const int n = tile0 + rr - I.row0;
+                        row0 = I.row0;
+                        deg = I.rowptr[n + 1] - I.rowptr[n];
+                        cp = I.colidx + I.rowptr[n];
+                    }
+                }
+                const int degm = max(deg, __shfl_xor_sync(0xffffffffu, deg, 16));
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j0 = 0; j0 < degm; j0 += 16) {
+                    int bit = 0;
+                    if (j0 + l < deg) bit = seed_bit((int64_t)row0 + cp[j0 + l]);
+                    const unsigned mine = (__ballot_sync(0xffffffffu, bit) >> (lane & 16)) & 0xFFFFu;
+                    const int nj = min(16, deg - j0);
+                    for (int j = 0; j < nj; ++j) {
+                        const float4 v = ((mine >> j) & 1u) ? zip1 : zip0;
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                }
+                finish_row(rr, rr < nrows, acc);
+            }
+        } else {
             if (single) {
                 int it = draw_item();
                 while (it < 64) {
@@ -584,21 +662,26 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),
                          w32 = lds4((const unsigned char*)W3s, 512 + 16 * l), w33 = lds4((const unsigned char*)W3s, 768 + 16 * l);
             float4 iv, rv, ipo;
-            load_own(hw, hw < nrows, iv, rv, ipo);
+            if (!ZS) load_own(hw, hw < nrows, iv, rv, ipo);
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
                 const int rr = hw + RSTEP * it;
                 const bool ok = rr < nrows;
                 float hv[4];
+                if (ZS) {                                    // I_0 = enc(I0), I'_0 of the row's kind; no R plane
+                    const bool sd = ok && kind_s[rr] != 0;
+                    iv = sd ? ze1 : ze0; ipo = sd ? zip1 : zip0; rv = iv;
+                }
                 update_row(rr, ok, lds4(Ls, off0 + it * PASS), iv, rv, ipo, w30, w31, w32, w33, hv);
-                if (it + 1 < 4) load_own(rr + RSTEP, rr + RSTEP < nrows, iv, rv, ipo);
+                if (!ZS && it + 1 < 4) load_own(rr + RSTEP, rr + RSTEP < nrows, iv, rv, ipo);
                 hid_bfly(rr, ok, hv);
             }
         }
         float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
         float4 hRg = hI;                                 // RF: hid(R_k) of row t
-        if (STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
-        if (RF && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
+        if (!ZS && STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
+        if (!ZS && RF && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
+        if (ZS) hRg = *reinterpret_cast<const float4*>(a.z_tbl + TB_HR);       // hid(R_0) = W3 enc(0)
         umma::fence_proxy_async();
         HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         // ---- P4: GEMM2 || metadata of the next tile || softmax of the input state ; I' epilogue (+ hid(I_{k+1}))
@@ -611,7 +694,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             *reinterpret_cast<float4*>(a.hid_r + (size_t)(tile0 + t) * 4) =
                 make_float4(fmaf(g, c.x, hRg.x), fmaf(g, c.y, hRg.y), fmaf(g, c.z, hRg.z), fmaf(g, c.w, hRg.w));
         }
-        if (STP(probs) != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
+        if (ZS && STP(probs) != nullptr && t < nrows) {     // probs[0] of the row's kind (decoder of the two rows: table)
+            const float* pk = a.z_tbl + TB_PR + 4 * kind_s[t];
+            float* pr = STP(probs) + (size_t)(tile0 + t) * 3;
+            pr[0] = pk[0]; pr[1] = pk[1]; pr[2] = pk[2];
+        }
+        if (!ZS && STP(probs) != nullptr && t < nrows) {    // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
             const float4 hR = RF ? hRg : *reinterpret_cast<const float4*>(hr_s + 4 * t);
             const float4 b3v = *reinterpret_cast<const float4*>(small);
