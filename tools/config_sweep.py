@@ -68,6 +68,12 @@ def real_graph(name):
     return scipy.sparse.csr_matrix((np.ones(len(ix), dtype=np.int64), ix, ip), shape=(n, n))
 
 
+if "--small" in sys.argv:       # the latency-bound batches only (at most one tile per pipeline): hub-relay threshold A/B
+    for name, Bs in (("karate", (1, 8)), ("fb-food", (8, 32)), ("fb-social", (8, 16)), ("openflights", (8,)), ("wiki-vote", (2, 4))):
+        for B in Bs:
+            run(name + " (real)", real_graph(name), B, 20, reps=10)
+    sys.exit(0)
+
 ep = synth.epinions_standin(0)
 print("--- shipped real graphs (reference real_graphs/*.pkl, largest connected component)")
 run("karate (real)", real_graph("karate"), 1, 20)
