@@ -49,8 +49,8 @@ struct StreamCfg {
     static constexpr int P_HR = P_HS + TR * 16;            // hid(R_k) / W3 I'_k [TR][4]
     static constexpr int P_CI = P_HR + TR * 16;            // colidx slice + 64 B over-read pad
     static constexpr int P_PM = P_CI + CAP * 4 + 64;       // work items of the gather: [64] x {a, b | c, d} tile rows (256 B)
-    static constexpr int P_ZK = P_PM;                      // step 0 from descriptors (no work items, no staged colidx slice):
-    static constexpr int P_ZI = P_CI;                      // seed flag [TR] and instance [TR] of every tile row
+    static constexpr int P_ZK = P_PM;                      // step 0 from descriptors (no work items): seed flag of every tile row [TR]
+    static constexpr int P_ZI = P_CI;                      // and, in tiles that span instances (no staged colidx slice), its instance [TR]
     static constexpr int P_BYTES = ((P_PM + 256 + 1023) / 1024) * 1024;
     static constexpr int TOTAL = D_SHARED + 2 * P_BYTES + 1024;
     static constexpr int TMEM_COLS = 512;                 // two [128 x 160] fp32 accumulators, 256 columns apart
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (!ZS && single && t < 64) pmv = __ldg(reinterpret_cast<const uint32_t*>(a.bv.tile_perm) + (size_t)(tile0 / TR) * 64 + t);
             const int ecnt = min(m.ecnt, C::CAP);
             if (single && t <= nrows) rpv = __ldg(m.rowptr + t);
-            if (!ZS && single) {
+            if (single) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) civ[u] = __ldg(m.colidx + ebase + t + u * PT);
             }
@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                     sts4(Xs, off0 + i * PASS, s0);
                     sts4(Ls, off0 + i * PASS, umma::tf32_trunc_lo4(s0));
                 }
-                if (t < nrows) { kind_s[t] = (unsigned char)zk; zinst_s[t] = zi; bg_s[t] = bgv; bg_s[TR + t] = zg; }
+                if (t < nrows) { kind_s[t] = (unsigned char)zk; bg_s[t] = bgv; bg_s[TR + t] = zg; }
+                if (t < nrows && !single) zinst_s[t] = zi;            // (aliases the colidx slice, which only single tiles stage)
             }
 #pragma unroll
             for (int i = 0; i < ((OPT & 8) || ZS ? 0 : 4); ++i) {
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             if (t < TR / 32) hub_mask[t] = 0u;
             if (single && t <= nrows) rp_s[t] = rpv;
             if (!ZS && single && t < 64) reinterpret_cast<uint32_t*>(hb + C::P_PM)[t] = pmv;
-            if (!ZS && single) {
+            if (single) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = civ[u];   // instance-local ids
             }
@@ -399,6 +400,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         // ---- P2: GEMM1 ; S' epilogue (+ hid(S_k))
         if (t == 0) issue_gemm();
         if (relay && t < nrows && rp_s[t + 1] - rp_s[t] > C::HUB_DEG) atomicOr(&hub_mask[t >> 5], 1u << (t & 31));
+        if (ZS && single) {
+            // step 0 from descriptors: the staged column indices are replaced by the seed bits of those neighbours, all
+            // looked up together while GEMM1 runs; the neighbour sums below then read shared memory only
+            const int ecnt = min(m.ecnt, C::CAP);
+            int zb[3] = {0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) zb[u] = seed_bit((int64_t)i_row0 + ci_s[t + u * PT]);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) if (t + u * PT < ecnt) ci_s[t + u * PT] = zb[u];
+        }
         // work items of the neighbour gather (gnode_batch_create): strided over the warps when the tile's CSR slice fits the
         // staged window, shared-memory tickets for hub tiles so that a long row does not leave the other warps idle
         const float* lane_base = STP(ip_in) + (size_t)i_row0 * H + 4 * l;
@@ -522,10 +533,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 const int rr = hw + RSTEP * it;
                 int deg = 0, row0 = i_row0;
                 const int32_t* cp = nullptr;
+                const int* fl = nullptr;                     // seed bits of the row's neighbours in shared memory, or null
                 if (rr < nrows) {
                     if (single) {
                         deg = rp_s[rr + 1] - rp_s[rr];
                         cp = m.colidx + rp_s[rr];
+                        const int e_rel = rp_s[rr] - ebase;
+                        if (e_rel + deg <= C::CAP) fl = ci_s + e_rel;
                     } else {
                         const GnInstance I = a.bv.inst[zinst_s[rr]];
                         const int n = tile0 + rr - I.row0;
@@ -538,7 +552,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int j0 = 0; j0 < degm; j0 += 16) {
                     int bit = 0;
-                    if (j0 + l < deg) bit = seed_bit((int64_t)row0 + cp[j0 + l]);
+                    if (j0 + l < deg) bit = fl ? fl[j0 + l] : seed_bit((int64_t)row0 + cp[j0 + l]);
                     const unsigned mine = (__ballot_sync(0xffffffffu, bit) >> (lane & 16)) & 0xFFFFu;
                     const int nj = min(16, deg - j0);
                     for (int j = 0; j < nj; ++j) {
