@@ -175,8 +175,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
     constexpr bool ZS = (OPT & 128) != 0;
     static_assert(!ZS || (RF && !PERSIST && (OPT & 64)), "step 0 from descriptors: inference without an R plane, one launch, raw S tile");
     constexpr int PT = C::PT, TR = C::TR, RSTEP = C::RSTEP, PASS = C::PASS;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    // The dynamic shared memory of this kernel starts at a 1024-byte boundary of the shared window (declared so, and
+    // checked once): with a base the compiler knows, every operand-tile address is the symbol plus a constant instead of
+    // an alignment term that was rematerialised (S2UR SR_CgaCtaId, ULEA, ULOP3 ...) at 23 places of the 64-register kernel.
+    extern __shared__ __align__(1024) unsigned char smem_al[];
+    unsigned char* smem = smem_al;
+    if ((umma::smem_u32(smem_al) & 1023u) != 0u) __trap();
     const int tid = threadIdx.x;
     const int half = __shfl_sync(0xffffffffu, tid / PT, 0);          // pipeline index, provably warp-uniform
     const int t = tid & (PT - 1), lane = t & 31;

@@ -127,8 +127,11 @@ __device__ __forceinline__ void tf32_split4(float4 x, float4& hi, float4& lo) {
 // Truncation split (the pipelined step kernels): tcgen05.mma kind::tf32 reads only the top 19 bits of a 32-bit element
 // (tools/umma_lowbits_probe.cu), so a raw fp32 word IS the operand hi = trunc_tf32(x): nothing is converted or written
 // back. lo = rna_tf32(x - hi); x - hi has up to 13 significant bits, so |x - hi - lo| <= 2^-21 |x| (rna split: 2^-22).
+// (cvt.rna.tf32.f32 is emulated on sm_100a: an Inf/NaN test, a predicated add of half an ulp, a mask. The residual is
+// finite and tiny, so the add and the mask are applied directly: the same bits, one instruction less per element.)
 __device__ __forceinline__ float tf32_trunc_lo(float x) {
-    return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+    const float d = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float4 tf32_trunc_lo4(float4 x) {
     return make_float4(tf32_trunc_lo(x.x), tf32_trunc_lo(x.y), tf32_trunc_lo(x.z), tf32_trunc_lo(x.w));

@@ -10,7 +10,11 @@ the slowest warp of the PREVIOUS phase.
 import collections, csv, re, sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+nxt = [i for i, r in enumerate(rows) if i > 0 and r and r[0] == "Kernel Name"]     # several launches: the first one only
+if nxt:
+    rows = rows[:nxt[0]]
 min_share = float(sys.argv[2]) if len(sys.argv) > 2 else 0.4
+n_rows = int(sys.argv[3]) if len(sys.argv) > 3 else 0                              # rows of the launch: instructions per row
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[2:] if len(r) >= len(hdr)]
@@ -32,4 +36,6 @@ for a, b in seg:
         for h in stalls:
             c[h] += float(r[ix[h]] or 0)
     top = ", ".join("%s %.1f" % (k.replace("stall_", ""), 100 * v / total) for k, v in c.most_common(5))
-    print("SASS %5d-%5d  %5.1f %%  | %s" % (a, b, 100 * n / total, top))
+    inst = sum(float(r[ix["Instructions Executed"]] or 0) for r in data[a:b + 1])
+    per_row = "  %5.1f warp-instr/row" % (inst / n_rows) if n_rows else ""
+    print("SASS %5d-%5d  %5.1f %%%s  | %s" % (a, b, 100 * n / total, per_row, top))
