@@ -462,10 +462,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
 
         const bool dec = RF || STP(probs) != nullptr;
         // own-row operands that still come from HBM/L2: I_k, I'_k (and R_k when the R plane is carried)
-        auto load_own = [&](int rr, bool ok, float4& iv, float4& rv, float4& ipo) {
-            iv = make_float4(1.f, 1.f, 1.f, 1.f); rv = iv; ipo = iv;
+        // (`off` = float offset of the lane's chunk of the row in a state / I' plane; rows that do not exist keep whatever
+        // the registers hold: update_row never reads them)
+        auto load_own = [&](size_t off, bool ok, float4& iv, float4& rv, float4& ipo) {
             if (ok) {
-                const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
                 iv = ldg4_hint(STP(y_in) + plane + off, pol_stream);
                 if (!RF) rv = ldg4_hint(STP(y_in) + 2 * plane + off, pol_stream);
                 ipo = ldg4_hint(STP(ip_in) + off, pol_keep);
@@ -473,12 +473,11 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         };
         // SIR update of tile row rr from tp = AI * S' (`ok` is uniform per half-warp): stores S,I(,R)_{k+1}; I_{k+1}
         // raw / lo -> operand tiles; returns the lane's partial linear3 products of R_k (RF: of I'_k) in hv
-        auto update_row = [&](int rr, bool ok, float4 tp, float4 iv, float4 rv, float4 ipo,
+        auto update_row = [&](int rr, size_t off, bool ok, float4 tp, float4 iv, float4 rv, float4 ipo,
                               float4 w30, float4 w31, float4 w32, float4 w33, float (&hv)[4]) {
             hv[0] = 0.f; hv[1] = 0.f; hv[2] = 0.f; hv[3] = 0.f;
             if (ok) {
                 const int o = C::sw(rr, l);
-                const size_t off = (size_t)(tile0 + rr) * H + 4 * l;
                 const float4 s = (OPT & 64) ? lds4(Xs, o) : tf32_unpack4(lds4(Xs, o));
                 const float nbe = -bg_s[rr], ga = bg_s[TR + rr];
                 float4 sn, in_, rn;
@@ -679,8 +678,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             //      lane's 4 x 4 linear3 weights stay in registers for the four passes)
             const float4 w30 = lds4((const unsigned char*)W3s, 16 * l), w31 = lds4((const unsigned char*)W3s, 256 + 16 * l),
                          w32 = lds4((const unsigned char*)W3s, 512 + 16 * l), w33 = lds4((const unsigned char*)W3s, 768 + 16 * l);
-            float4 iv, rv, ipo;
-            if (!ZS) load_own(hw, hw < nrows, iv, rv, ipo);
+            float4 iv = make_float4(1.f, 1.f, 1.f, 1.f), rv = iv, ipo = iv;
+            size_t off_own = (size_t)(tile0 + hw) * H + 4 * l;       // this half-warp's row of the pass, advanced by RSTEP rows
+            if (!ZS) load_own(off_own, hw < nrows, iv, rv, ipo);
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
                 const int rr = hw + RSTEP * it;
@@ -690,8 +690,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                     const bool sd = ok && kind_s[rr] != 0;
                     iv = sd ? ze1 : ze0; ipo = sd ? zip1 : zip0; rv = iv;
                 }
-                update_row(rr, ok, lds4(Ls, off0 + it * PASS), iv, rv, ipo, w30, w31, w32, w33, hv);
-                if (!ZS && it + 1 < 4) load_own(rr + RSTEP, rr + RSTEP < nrows, iv, rv, ipo);
+                update_row(rr, off_own, ok, lds4(Ls, off0 + it * PASS), iv, rv, ipo, w30, w31, w32, w33, hv);
+                off_own += (size_t)RSTEP * H;
+                if (!ZS && it + 1 < 4) load_own(off_own, rr + RSTEP < nrows, iv, rv, ipo);
                 hid_bfly(rr, ok, hv);
             }
         }
