@@ -42,8 +42,8 @@ struct StepArgs {
     int64_t ldx;
     float* probs;         // [M][3] slice of the produced state (dual kernel: of the INPUT state), or null
     float* hid_i;         // [M][4] linear3 pre-activations (no bias) of the I block: ENCODE writes I_0's, the dual step kernel updates in place; or null
-    float* hid_r;         // [M][4] inference without an R plane (dual kernel, RF): linear3 pre-activations of the R block, carried by
-                          // linearity (hid(R_{k+1}) = hid(R_k) + dt gamma W3 I'_k); ENCODE writes R_0's; null = R is a full state plane
+    float* hid_r;         // [M][4] inference without an R plane (RF): W3 (S_0 + I_0 + R_0), constant over the rollout; hid(R_k) follows by
+                          // the conserved sum (hid(R_k) = hid_r - hid(S_k) - hid(I_k)); ENCODE writes it; null = R is a full state plane
     float dt;
     long long* tbuf;      // phase timing accumulators (debug, env GNODE_DBG bit 7) or null
     int dbg;              // timing experiments only (env GNODE_DBG): bit0 no decode, 1 no gather, 2 no own loads, 3 no GEMM2, 4 no GEMM1
@@ -121,10 +121,13 @@ __device__ __forceinline__ void decode_row(float4 s, float4 i, float4 r, const f
 #pragma unroll
         for (int m = 0; m < 12; ++m) v[m] += __shfl_xor_sync(0xffffffffu, v[m], off);
     if (l == 0 && valid && hid_i_row != nullptr) *reinterpret_cast<float4*>(hid_i_row) = make_float4(v[4], v[5], v[6], v[7]);
-    if (l == 0 && valid && hid_r_row != nullptr) *reinterpret_cast<float4*>(hid_r_row) = make_float4(v[8], v[9], v[10], v[11]);
-    if (l == 0 && valid && hid_r_in != nullptr) {      // R is carried as its four hidden pre-activations only
+    // inference without an R plane: the row keeps hid(S_0 + I_0 + R_0) (written here by the encoder launch), and
+    // hid(R_k) = that - hid(S_k) - hid(I_k) wherever probabilities are emitted (S + I + R is conserved, see the step kernels)
+    if (l == 0 && valid && hid_r_row != nullptr)
+        *reinterpret_cast<float4*>(hid_r_row) = make_float4((v[0] + v[4]) + v[8], (v[1] + v[5]) + v[9], (v[2] + v[6]) + v[10], (v[3] + v[7]) + v[11]);
+    if (l == 0 && valid && hid_r_in != nullptr) {
         const float4 h = *reinterpret_cast<const float4*>(hid_r_in);
-        v[8] = h.x; v[9] = h.y; v[10] = h.z; v[11] = h.w;
+        v[8] = (h.x - v[0]) - v[4]; v[9] = (h.y - v[1]) - v[5]; v[10] = (h.z - v[2]) - v[6]; v[11] = (h.w - v[3]) - v[7];
     }
     if (l == 0 && valid && probs_row != nullptr) {
         const float* b3 = small; const float* w2 = small + 4; const float b2 = small[8];
@@ -1003,7 +1006,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                 }
             };
             load_own(0);
-            const bool dec = (RF || STP(probs) != nullptr) && !(a.dbg & 8192);
+            const bool dec = !RF && STP(probs) != nullptr && !(a.dbg & 8192);   // RF: hid(R_k) follows from the conserved sum (P4)
             const bool b3 = (l & 8) != 0, b2 = (l & 4) != 0;
             const float4 w30 = *reinterpret_cast<const float4*>(W3s + 0 * H + 4 * l), w31 = *reinterpret_cast<const float4*>(W3s + 1 * H + 4 * l),
                          w32 = *reinterpret_cast<const float4*>(W3s + 2 * H + 4 * l), w33 = *reinterpret_cast<const float4*>(W3s + 3 * H + 4 * l);
@@ -1036,8 +1039,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                     }
                     sts4(Xs, off0 + it * PASS, in_);             // operand of GEMM2 (raw = hi, truncation split)
                     sts4(Ls, off0 + it * PASS, umma::tf32_trunc_lo4(in_));
-                    if (dec) {                                   // partial linear3 products of R_k (RF: of I'_k) over this lane's 4 channels
-                        const float4 dv = RF ? ipo : rv;
+                    if (dec) {                                   // partial linear3 products of R_k over this lane's 4 channels
+                        const float4 dv = rv;
                         hv0 = dot4(dv, w30); hv1 = dot4(dv, w31); hv2 = dot4(dv, w32); hv3 = dot4(dv, w33);
                     }
                 }
@@ -1055,9 +1058,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         }
         GN_TICK(3)
         float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
-        float4 hRg = hI;                                 // RF: hid(R_k) of row t
+        float4 hRg = hI;                                 // RF: hid(S_0 + I_0 + R_0) of row t (constant over the rollout)
         if (STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
-        if (RF && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
+        if (RF && STP(probs) != nullptr && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
         umma::fence_proxy_async();
         HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         GN_TICK(4)
@@ -1066,17 +1069,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
         if (do_g2 && t == 0) umma::issue_split_gemm160<TR>(tmem, mbar, wop, xs_addr, ls_addr);
         if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
-        if (RF && t < nrows) {
-            // R_{k+1} = R_k + dt gamma I'_k is linear and R feeds nothing but the decoder's linear3: the row carries
-            // hid(R) = W3 R (4 floats) instead of the 64-float R plane; hr_s holds W3 I'_k of the row
-            const float4 c = *reinterpret_cast<const float4*>(hr_s + 4 * t);
-            const float g = __fmul_rn(STP(dt), bg_s[TR + t]);
-            *reinterpret_cast<float4*>(a.hid_r + (size_t)(tile0 + t) * 4) =
-                make_float4(fmaf(g, c.x, hRg.x), fmaf(g, c.y, hRg.y), fmaf(g, c.z, hRg.z), fmaf(g, c.w, hRg.w));
-        }
         if (STP(probs) != nullptr && t < nrows) {           // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
-            const float4 hR = RF ? hRg : *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            // RF: R feeds nothing but the decoder's linear3 and S + I + R is conserved channel by channel (dS + dI + dR = 0,
+            // ode_nn_ngraph_sim.py:75-77): hid(R_k) = W3 (S_0 + I_0 + R_0) - hid(S_k) - hid(I_k), the first term written once
+            // by the encoder launch (4 floats per row), the other two riding on the transform's GEMMs
+            const float4 hR = RF ? make_float4((hRg.x - hS.x) - hI.x, (hRg.y - hS.y) - hI.y, (hRg.z - hS.z) - hI.z, (hRg.w - hS.w) - hI.w)
+                                 : *reinterpret_cast<const float4*>(hr_s + 4 * t);
             const float4 b3v = *reinterpret_cast<const float4*>(small);
             const float4 w2v = *reinterpret_cast<const float4*>(small + 4);
             const float b2v = small[8];
@@ -1277,11 +1276,14 @@ static int step_kernel_choice() {
     return g_step_kernel;
 }
 
-// Inference (no stored trajectory) with the default dual kernel carries R as hid(R) = W3 R, four floats per row, instead
-// of a 64-float state plane: R_{k+1} = R_k + dt gamma I'_k is linear in I' and R feeds nothing but the decoder's linear3
-// (ode_nn_ngraph_sim.py:77,172-176), so hid(R_{k+1}) = hid(R_k) + dt gamma (W3 I'_k). 512 of the 2060 algorithmic bytes
-// per node-step are not moved; the roofline denominator stays 2060. GNODE_R_STATE=full / gnode_set_r_state(0)
-// keeps the R plane (bitwise the training forward); training always stores R (the decoder's weight gradient needs it).
+// Inference (no stored trajectory) with the pipelined step kernels carries no R plane at all: R feeds nothing but the
+// decoder's linear3 (ode_nn_ngraph_sim.py:172-176) and dS + dI + dR = 0 (:75-77), i.e. S + I + R is conserved channel by
+// channel, so hid(R_k) = W3 (S_0 + I_0 + R_0) - hid(S_k) - hid(I_k). The first term is four floats per row written once by
+// the encoder launch, the other two ride on the transform's GEMMs: nothing of R is computed, read or written per step.
+// (Until round 3 hid(R) was advanced by linearity, hid(R_{k+1}) = hid(R_k) + dt gamma W3 I'_k: 16 FMAs, a butterfly and
+// a 32-byte read-modify-write per row and step, 4 % of the step.) 512 of the 2060 algorithmic bytes per node-step are not
+// moved; the roofline denominator stays 2060. GNODE_R_STATE=full / gnode_set_r_state(0) keeps the R plane
+// (bitwise the training forward); training always stores R (the decoder's weight gradient needs it).
 static int g_r_state = -1;
 static int r_state_choice() {
     if (g_r_state < 0) { const char* e = getenv("GNODE_R_STATE"); g_r_state = (e && (!strcmp(e, "full") || !strcmp(e, "0"))) ? 0 : 1; }

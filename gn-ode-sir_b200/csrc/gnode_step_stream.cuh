@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         umma::fence_before_sync();
         HSYNC();                                                                // S2
 
-        const bool dec = RF || STP(probs) != nullptr;
+        // the full-plane mode decodes R_k from its row; RF needs nothing per step: hid(R_k) follows from the conserved sum
+        const bool dec = !RF && STP(probs) != nullptr;
         // own-row operands that still come from HBM/L2: I_k, I'_k (and R_k when the R plane is carried)
         // (`off` = float offset of the lane's chunk of the row in a state / I' plane; rows that do not exist keep whatever
         // the registers hold: update_row never reads them)
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 else sts4(Xs, o, tf32_pack4(in_, ilo));              // hi operand of GEMM2 (packed like the S tile)
                 sts4(Ls, o, ilo);
                 if (dec) {
-                    const float4 dv = RF ? ipo : rv;
+                    const float4 dv = rv;
                     hv[0] = dot4(dv, w30); hv[1] = dot4(dv, w31); hv[2] = dot4(dv, w32); hv[3] = dot4(dv, w33);
                 }
             }
@@ -697,22 +698,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
             }
         }
         float4 hI = make_float4(0.f, 0.f, 0.f, 0.f);     // hid(I_k) of row t (softmax threads): in flight across the barrier
-        float4 hRg = hI;                                 // RF: hid(R_k) of row t
+        float4 hRg = hI;                                 // RF: hid(S_0 + I_0 + R_0) of row t (constant over the rollout)
         if (!ZS && STP(probs) != nullptr && t < nrows) hI = *reinterpret_cast<const float4*>(a.hid_i + (size_t)(tile0 + t) * 4);
-        if (!ZS && RF && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
-        if (ZS) hRg = *reinterpret_cast<const float4*>(a.z_tbl + TB_HR);       // hid(R_0) = W3 enc(0)
+        if (!ZS && RF && STP(probs) != nullptr && t < nrows) hRg = *reinterpret_cast<const float4*>(a.hid_r + (size_t)(tile0 + t) * 4);
+        if (ZS) hRg = *reinterpret_cast<const float4*>(a.z_tbl + TB_HR);       // the same for both kinds of rows
         umma::fence_proxy_async();
         HSYNC();                                                                // S3 (every thread has read its copy of *meta)
         // ---- P4: GEMM2 || metadata of the next tile || softmax of the input state ; I' epilogue (+ hid(I_{k+1}))
         if (t == 0) issue_gemm();
         if (t == PT - 32) fetch_meta(kfetch);
         ++kfetch;
-        if (RF && t < nrows) {
-            const float4 c = *reinterpret_cast<const float4*>(hr_s + 4 * t);
-            const float g = __fmul_rn(dt, bg_s[TR + t]);
-            *reinterpret_cast<float4*>(a.hid_r + (size_t)(tile0 + t) * 4) =
-                make_float4(fmaf(g, c.x, hRg.x), fmaf(g, c.y, hRg.y), fmaf(g, c.z, hRg.z), fmaf(g, c.w, hRg.w));
-        }
+        if (ZS && t < nrows) *reinterpret_cast<float4*>(a.hid_r + (size_t)(tile0 + t) * 4) = hRg;   // written once, read when probs are emitted
         if (ZS && STP(probs) != nullptr && t < nrows) {     // probs[0] of the row's kind (decoder of the two rows: table)
             const float* pk = a.z_tbl + TB_PR + 4 * kind_s[t];
             float* pr = STP(probs) + (size_t)(tile0 + t) * 3;
@@ -720,7 +716,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         }
         if (!ZS && STP(probs) != nullptr && t < nrows) {    // one thread per row: probs[k] = softmax(decoder(S_k, I_k, R_k))
             const float4 hS = *reinterpret_cast<const float4*>(hs_s + 4 * t);
-            const float4 hR = RF ? hRg : *reinterpret_cast<const float4*>(hr_s + 4 * t);
+            // RF: S + I + R is conserved channel by channel (dS + dI + dR = 0, ode_nn_ngraph_sim.py:75-77), so
+            // hid(R_k) = W3 (S_0 + I_0 + R_0) - hid(S_k) - hid(I_k): no R plane and no per-step recurrence
+            const float4 hR = RF ? make_float4((hRg.x - hS.x) - hI.x, (hRg.y - hS.y) - hI.y, (hRg.z - hS.z) - hI.z, (hRg.w - hS.w) - hI.w)
+                                 : *reinterpret_cast<const float4*>(hr_s + 4 * t);
             const float4 b3v = *reinterpret_cast<const float4*>(small);
             const float4 w2v = *reinterpret_cast<const float4*>(small + 4);
             const float b2v = small[8];
