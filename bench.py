@@ -37,9 +37,10 @@ H = 64
 MAXTIME, DELTAT = 20, 0.5
 ALGO_BYTES_PER_NODE_STEP = 2060.0      # SURVEY 8d / BASELINE.md section 3 (fixed denominator)
 R_STATE_NOTE = {
-    1: "inference carries R as hid(R) = W3 R (4 floats per row, exact by linearity of R' = gamma I'); the 64-float R plane is "
-       "neither read nor written, i.e. 512 of the 2060 algorithmic bytes per node-step are not moved -- the roofline denominator "
-       "stays 2060 B (SURVEY 8d); GNODE_R_STATE=full keeps the plane",
+    1: "inference carries no R plane: S + I + R is conserved (dS + dI + dR = 0), so the decoder's R term is "
+       "W3 (S_0 + I_0 + R_0) - W3 S_k - W3 I_k (4 floats per row written once + two terms the transform's GEMMs deliver); the "
+       "64-float R plane is neither read nor written, i.e. 512 of the 2060 algorithmic bytes per node-step are not moved -- the "
+       "roofline denominator stays 2060 B (SURVEY 8d); GNODE_R_STATE=full keeps the plane",
     0: "full 64-float R plane (GNODE_R_STATE=full)"}
 JSON_OUT = sys.stdout
 UNIT = "node-steps/s"

@@ -87,12 +87,13 @@ int gnode_get_variant(void);
  * set them before launching work from several threads, not concurrently with it. */
 int gnode_set_step_kernel(int kernel);
 int gnode_get_step_kernel(void);
-/* How inference rollouts (traj == NULL, default step kernel) carry the R block. 1 (default) = as its four linear3
- * pre-activations hid(R) = W3 R per row: R_{k+1} = R_k + dt gamma I'_k (ode_nn_ngraph_sim.py:77 + the Euler update)
- * is linear in I' and R feeds only the decoder's linear3 (:172-176), so hid(R_{k+1}) = hid(R_k) + dt gamma W3 I'_k
- * and the 64-float R plane is neither read nor written (512 B per node-step less traffic; probabilities agree with
- * the full-plane path to fp32 rounding, ~1e-7). 0 = full R plane, bitwise the training forward. Env GNODE_R_STATE=full
- * selects 0. Training (traj != NULL) always stores R. */
+/* How inference rollouts (traj == NULL, default step kernel) carry the R block. 1 (default) = not at all: R feeds only
+ * the decoder's linear3 (ode_nn_ngraph_sim.py:172-176) and dS + dI + dR = 0 (:75-77), i.e. S + I + R is conserved channel
+ * by channel, so the decoder's pre-activations of R_k are W3 (S_0 + I_0 + R_0) - W3 S_k - W3 I_k: four floats per row
+ * written once by the encoder launch, minus two terms the transform's GEMMs deliver anyway. The 64-float R plane is
+ * neither read nor written and nothing of R is computed per step (512 B per node-step less traffic; probabilities agree
+ * with the full-plane path to fp32 rounding, < 1e-6 on the goldens). 0 = full R plane, bitwise the training forward.
+ * Env GNODE_R_STATE=full selects 0. Training (traj != NULL) always stores R. */
 int gnode_set_r_state(int hidden);
 int gnode_get_r_state(void);
 /* Rollout launch structure of the tensor-core step kernels: 1 = ONE cooperative launch runs all Euler steps with a grid

@@ -257,8 +257,8 @@ def r_state(gn):
 
 @pytest.mark.parametrize("name", STRICT_CASES)
 def test_inference_r_state_modes(gn, r_state, name):
-    """Inference carries R either as a 64-float plane (0: the training forward's arithmetic) or as hid(R) = W3 R
-    (1, default: hid(R_{k+1}) = hid(R_k) + dt gamma W3 I'_k). Both meet the 1e-5 bar against the reference's own
+    """Inference carries R either as a 64-float plane (0: the training forward's arithmetic) or not at all (1, default:
+    S + I + R is conserved, so hid(R_k) = W3 (S_0 + I_0 + R_0) - hid(S_k) - hid(I_k)). Both meet the 1e-5 bar against the reference's own
     outputs and agree with each other to fp32 rounding; the S and I dynamics are bitwise the same, so only the R
     logit differs."""
     g = Golden(name)
