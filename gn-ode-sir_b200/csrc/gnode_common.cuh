@@ -140,6 +140,21 @@ __device__ __forceinline__ int sw_off(int r, int c4) {
     return ((c4 >> 3) << 14) + (r << 7) + ((((c4 & 7) ^ (r & 7))) << 4);
 }
 
+// ---- packed fp32 pairs (sm_100: add / mul / fma .f32x2, SASS FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations
+// per instruction -- the same bits as the scalar form, half the issue slots. The step kernels are bound by their chain of
+// dependent phases and by issue slots, not by the FP32 pipe, so the row sums, the SIR update and the sigmoid run on pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// acc += v, component by component (the sequential row sums: same additions, same order)
+__device__ __forceinline__ void add4(float4& acc, const float4& v) {
+    unpack2(add2(pack2(acc.x, acc.y), pack2(v.x, v.y)), acc.x, acc.y);
+    unpack2(add2(pack2(acc.z, acc.w), pack2(v.z, v.w)), acc.z, acc.w);
+}
+
 __device__ __forceinline__ float4 lds4(const unsigned char* base, int off) {
     return *reinterpret_cast<const float4*>(base + off);
 }
@@ -204,6 +219,32 @@ __device__ __forceinline__ float sigmoid_t(float z) {
     } else {
         return 1.0f / (1.0f + expf(-z));
     }
+}
+
+// The same sigmoid on a pair. FAST: op for op the scalar code above as the compiler emits it (the final 1 + e f is an FMA
+// there), with the negations folded into the constants: fma(z, -c, th) = -fma(z, c, -th) exactly (it is the exact residual
+// of the product) and fma(-tl, -ln2, 1) = fma(tl, ln2, 1) -- the same bits (tests/test_variants_gpu.py compares the kernels
+// that use the pair form with the one that uses the scalar form).
+template <bool FAST>
+__device__ __forceinline__ f32x2 sigmoid2_t(f32x2 z) {
+    float z0, z1;
+    if (FAST) {
+        const float c = -1.4426950408889634f, clo = -1.9259629911266175e-08f, ln2 = 0.6931471805599453f;
+        const f32x2 th = mul2(z, pack2(c, c));
+        const f32x2 r = fma2(z, pack2(-c, -c), th);
+        const f32x2 ntl = fma2(z, pack2(-clo, -clo), r);
+        const f32x2 f = fma2(ntl, pack2(-ln2, -ln2), pack2(1.0f, 1.0f));
+        unpack2(th, z0, z1);
+        float e0, e1, r0, r1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+        unpack2(fma2(pack2(e0, e1), f, pack2(1.0f, 1.0f)), z0, z1);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(z0));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(z1));
+        return pack2(r0, r1);
+    }
+    unpack2(z, z0, z1);
+    return pack2(sigmoid_t<false>(z0), sigmoid_t<false>(z1));
 }
 
 }  // namespace gnode

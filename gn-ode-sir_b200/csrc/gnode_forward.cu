@@ -559,7 +559,7 @@ __device__ __forceinline__ void gather_block(float4& acc, const float* __restric
         if (j0 + k < deg) v[k] = ldg4_hint(lane_base + (size_t)(unsigned)cp[j0 + k] * H, pol);
     }
 #pragma unroll
-    for (int k = 0; k < 4 * NB; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    for (int k = 0; k < 4 * NB; ++k) add4(acc, v[k]);
 }
 
 // Warp-uniform neighbour sum (both half-warps run the trip counts of the larger degree, loads predicated per row);
@@ -588,7 +588,7 @@ __device__ __forceinline__ void gather_exact(float4& acc, const float* __restric
         v[k] = ldg4_hint(lane_base + (size_t)(unsigned)c * H, pol);
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    for (int k = 0; k < K; ++k) add4(acc, v[k]);
 }
 
 // Warp-uniform neighbour sum specialised by the pair's larger degree (1..12 in one round trip, longer rows in
@@ -948,13 +948,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_dual_kernel(const __grid_co
                                 }
                                 if (lane < 16) {
 #pragma unroll
-                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                    for (int k = 0; k < 8; ++k) add4(sum, v[k]);
                                 }
                                 sum.x = __shfl_sync(0xffffffffu, sum.x, l); sum.y = __shfl_sync(0xffffffffu, sum.y, l);
                                 sum.z = __shfl_sync(0xffffffffu, sum.z, l); sum.w = __shfl_sync(0xffffffffu, sum.w, l);
                                 if (lane >= 16) {
 #pragma unroll
-                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                    for (int k = 0; k < 8; ++k) add4(sum, v[k]);
                                     run[4 * l + 0] = sum.x; run[4 * l + 1] = sum.y; run[4 * l + 2] = sum.z; run[4 * l + 3] = sum.w;
                                     if (sr == n_sr - 1 && warp == PT / 32 - 1) sts4(Xs, C::sw(r, l), sum);
                                 }

@@ -132,9 +132,9 @@ __device__ __forceinline__ void gather_two_rows(const float* __restrict__ lane_b
     }
     sa = make_float4(0.f, 0.f, 0.f, 0.f); sb = sa;
 #pragma unroll
-    for (int k = 0; k < D; ++k) { sa.x += v[k].x; sa.y += v[k].y; sa.z += v[k].z; sa.w += v[k].w; }
+    for (int k = 0; k < D; ++k) add4(sa, v[k]);
 #pragma unroll
-    for (int k = 0; k < D; ++k) { sb.x += v[D + k].x; sb.y += v[D + k].y; sb.z += v[D + k].z; sb.w += v[D + k].w; }
+    for (int k = 0; k < D; ++k) add4(sb, v[D + k]);
 }
 __device__ __forceinline__ void gather_quad(const float* __restrict__ lane_base, const int* cpa, int da, const int* cpb, int db,
                                             int dmax, int zrow, uint64_t pol, float4& sa, float4& sb) {
@@ -441,8 +441,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         umma::mbar_wait_suspend(mbar, phase); phase ^= 1;
         umma::fence_after_sync();
         {
+            if (N160) {                                  // accumulator halves, bias and sigmoid on component pairs
+                f32x2 v2[8];
+                umma::tmem_ld16_sum2(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+                    float4 o;
+                    unpack2(sigmoid2_t<FAST>(add2(v2[2 * j], pack2(bb.x, bb.y))), o.x, o.y);
+                    unpack2(sigmoid2_t<FAST>(add2(v2[2 * j + 1], pack2(bb.z, bb.w))), o.z, o.w);
+                    sts4(Ls, C::sw(erow, 4 * cq + j), o);
+                }
+            } else {
             float v[16];
-            if (N160) umma::tmem_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v); else umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
@@ -450,6 +462,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
                 o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
                 sts4(Ls, C::sw(erow, 4 * cq + j), o);
+            }
             }
             if (cq == 0) {
                 float hv[4];
@@ -482,17 +495,31 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 const float4 s = (OPT & 64) ? lds4(Xs, o) : tf32_unpack4(lds4(Xs, o));
                 const float nbe = -bg_s[rr], ga = bg_s[TR + rr];
                 float4 sn, in_, rn;
-#define GN_COMP(c)                                                                  \
+                // dS = -beta (AI S'), dR = gamma I', dI = -dS - dR; y + dt dy, every product and sum rounded on its own
+                // (the reference rounds after every ATen op). The PRODUCTS run on component pairs; the sums stay scalar
+                // __fadd_rn: ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding) although both carry an
+                // explicit rounding mode -- seen in the SASS of the R-free instantiation, 2.7e-6 on the fb-food golden.
+                // dI = fl(-dS - dR) = -fl(dS + dR) and fl(dt dI) = fl(-dt fl(dS + dR)) (round-to-nearest is sign-symmetric):
+                // the same bits as the all-scalar form.
+                const f32x2 nbe2 = pack2(nbe, nbe), ga2 = pack2(ga, ga), dt2 = pack2(dt, dt), ndt2 = pack2(-dt, -dt);
+#define GN_COMP2(a, b)                                                              \
     {                                                                               \
-        const float dS = __fmul_rn(nbe, tp.c);                                      \
-        const float dR = __fmul_rn(ga, ipo.c);                                      \
-        const float dI = __fsub_rn(-dS, dR);                                        \
-        sn.c = __fadd_rn(s.c, __fmul_rn(dt, dS));                                   \
-        in_.c = __fadd_rn(iv.c, __fmul_rn(dt, dI));                                 \
-        rn.c = __fadd_rn(rv.c, __fmul_rn(dt, dR));                                  \
+        const f32x2 dS = mul2(nbe2, pack2(tp.a, tp.b));                             \
+        const f32x2 dR = mul2(ga2, pack2(ipo.a, ipo.b));                            \
+        float dSa, dSb, dRa, dRb, pa, pb;                                           \
+        unpack2(dS, dSa, dSb); unpack2(dR, dRa, dRb);                               \
+        const f32x2 u = pack2(__fadd_rn(dSa, dRa), __fadd_rn(dSb, dRb));            \
+        unpack2(mul2(dt2, dS), pa, pb);                                             \
+        sn.a = __fadd_rn(s.a, pa); sn.b = __fadd_rn(s.b, pb);                       \
+        unpack2(mul2(ndt2, u), pa, pb);                                             \
+        in_.a = __fadd_rn(iv.a, pa); in_.b = __fadd_rn(iv.b, pb);                   \
+        if (!RF) {                                                                  \
+            unpack2(mul2(dt2, dR), pa, pb);                                         \
+            rn.a = __fadd_rn(rv.a, pa); rn.b = __fadd_rn(rv.b, pb);                 \
+        }                                                                           \
     }
-                GN_COMP(x) GN_COMP(y) GN_COMP(z) GN_COMP(w)
-#undef GN_COMP
+                GN_COMP2(x, y) GN_COMP2(z, w)
+#undef GN_COMP2
                 stg4_hint(STP(y_out) + off, sn, pol_stream);
                 stg4_hint(STP(y_out) + plane + off, in_, pol_stream);
                 if (!RF) stg4_hint(STP(y_out) + 2 * plane + off, rn, pol_stream);
@@ -561,7 +588,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                     const int nj = min(16, deg - j0);
                     for (int j = 0; j < nj; ++j) {
                         const float4 v = ((mine >> j) & 1u) ? zip1 : zip0;
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        add4(acc, v);
                     }
                 }
                 finish_row(rr, rr < nrows, acc);
@@ -628,13 +655,13 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                                 }
                                 if (lane < 16) {
 #pragma unroll
-                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                    for (int k = 0; k < 8; ++k) add4(sum, v[k]);
                                 }
                                 sum.x = __shfl_sync(0xffffffffu, sum.x, l); sum.y = __shfl_sync(0xffffffffu, sum.y, l);
                                 sum.z = __shfl_sync(0xffffffffu, sum.z, l); sum.w = __shfl_sync(0xffffffffu, sum.w, l);
                                 if (lane >= 16) {
 #pragma unroll
-                                    for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                                    for (int k = 0; k < 8; ++k) add4(sum, v[k]);
                                     run[4 * l + 0] = sum.x; run[4 * l + 1] = sum.y; run[4 * l + 2] = sum.z; run[4 * l + 3] = sum.w;
                                 }
                                 __syncwarp();
@@ -737,8 +764,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
         umma::fence_after_sync();
         if (t == PT - 32) issue_s_load();                // GEMM2 has read Xs: the next tile's S_k rows may land there
         {
+            if (N160) {                                  // accumulator halves, bias and sigmoid on component pairs
+                f32x2 v2[8];
+                umma::tmem_ld16_sum2(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
+                    float4 o;
+                    unpack2(sigmoid2_t<FAST>(add2(v2[2 * j], pack2(bb.x, bb.y))), o.x, o.y);
+                    unpack2(sigmoid2_t<FAST>(add2(v2[2 * j + 1], pack2(bb.z, bb.w))), o.z, o.w);
+                    sts4(Ls, C::sw(erow, 4 * cq + j), o);
+                }
+            } else {
             float v[16];
-            if (N160) umma::tmem_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v); else umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
+            umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 16 * cq, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 bb = *reinterpret_cast<const float4*>(bs + 16 * cq + 4 * j);
@@ -746,6 +785,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) step_stream_kernel(const __grid_
                 o.x = sigmoid_t<FAST>(v[4 * j + 0] + bb.x); o.y = sigmoid_t<FAST>(v[4 * j + 1] + bb.y);
                 o.z = sigmoid_t<FAST>(v[4 * j + 2] + bb.z); o.w = sigmoid_t<FAST>(v[4 * j + 3] + bb.w);
                 sts4(Ls, C::sw(erow, 4 * cq + j), o);
+            }
             }
             if (cq == 0) {
                 float hv[4];

@@ -121,7 +121,7 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ src, cons
                     v[j] = (c >= 0) ? ldg4(src + (size_t)c * H + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+                for (int j = 0; j < 8; ++j) add4(acc, v[j]);
             }
         }
     }

@@ -314,6 +314,22 @@ __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(__uint_as_float(s[i]), __uint_as_float(r[i]));
 }
+// the same, summed on pairs: v2[i] = {s[2i] + r[2i], s[2i+1] + r[2i+1]}
+__device__ __forceinline__ void tmem_ld16_sum2(uint32_t taddr, f32x2 (&v2)[8]) {
+    uint32_t r[16], s[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]),
+                   "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
+                 : "r"(taddr + (uint32_t)NB80));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        v2[i] = add2(pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+}
 __device__ __forceinline__ void tmem_ld4_sum(uint32_t taddr, float (&v)[4]) {
     uint32_t r[4], s[4];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"

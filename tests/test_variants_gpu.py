@@ -132,6 +132,29 @@ def test_step_kernels_agree_on_training_trajectory(gn):
     assert torch.equal(out[5], out[3]) and torch.equal(out[6], out[3])
 
 
+@pytest.mark.parametrize("r_state", [0, 1], ids=["r-plane", "conserved-sum"])
+@pytest.mark.parametrize("persistent", [0, 1], ids=["launch-per-step", "cooperative"])
+@pytest.mark.parametrize("name", ["sim_fbfood_b2", "ng_mixed_b5"])
+def test_pipelined_kernels_are_bitwise_equal_in_inference(gn, name, persistent, r_state):
+    """The TMA-fed kernel evaluates row sums, products, accumulator sums and the sigmoid on packed fp32 pairs (FADD2 /
+    FMUL2 / FFMA2), the LDG-fed one in scalar form: the same IEEE operations, so the probabilities are bitwise equal in
+    every instantiation (with and without the R plane, one launch per step and cooperative). This is the test that catches
+    a fused multiply-add the scalar form does not have (ptxas fuses mul.rn.f32x2 + add.rn.f32x2)."""
+    from gn_ode_sir_b200 import _lib
+    L = _lib.lib()
+    g = Golden(name)
+    prev = L.gnode_get_step_kernel(), L.gnode_get_persistent(), L.gnode_get_r_state()
+    out = {}
+    try:
+        L.gnode_set_persistent(persistent); L.gnode_set_r_state(r_state)
+        for k in (3, 5):
+            _lib.check(L.gnode_set_step_kernel(k), "gnode_set_step_kernel")
+            out[k] = run_cuda(gn, g)
+    finally:
+        L.gnode_set_step_kernel(prev[0]); L.gnode_set_persistent(prev[1]); L.gnode_set_r_state(prev[2])
+    assert torch.equal(out[3], out[5])
+
+
 @pytest.mark.parametrize("persistent", [0, 1], ids=["launch-per-step", "cooperative"])
 @pytest.mark.parametrize("step_kernel", [3, 5, 6], indirect=True, ids=["dual", "stream", "stream-barrier"])
 @pytest.mark.parametrize("name", ["sim_fbfood_b2", "ng_mixed_b5", "sim_wikivote_b2"])
