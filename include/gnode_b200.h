@@ -182,7 +182,13 @@ int gnode_rollout_forward_sel(gnode_batch_t b, const float* x, int64_t ldx, cons
  *   beta[i], gamma[i]                    DEVICE fp32, one per instance.
  * gnode_expand_trials writes the five live columns {S0, I0, R0, beta, gamma} of every row into x [M, ldx] (ldx >= 5;
  * the remaining columns are not touched) -- the training path keeps that compact x for the reverse sweep.
- * gnode_rollout_forward_trials = expansion (ldx = GNODE_TRIAL_LDX, in the workspace) + gnode_rollout_forward_sel. */
+ * gnode_rollout_forward_trials gives the probabilities of expansion (ldx = GNODE_TRIAL_LDX, in the workspace) +
+ * gnode_rollout_forward_sel, bit for bit, without ever forming the dense block when it rolls out for inference
+ * (traj == NULL, T > 1, default step kernel and R state): every row of y_0 is one of two vectors, so the
+ * encoder, its transform and the decoder of grid point 0 are evaluated for two rows into a small table, a seed bitmap is
+ * set from the descriptors, and Euler step 0 runs from table + bitmap (neither y_0 nor I'_0 is written); cooperative
+ * rollouts of small batches keep an encoder launch, which is then a stream of stores. Env GNODE_TRIALS_ENCODE=dense | fill
+ * selects the expansion path / the store-stream encoder for A/B. The workspace size is the same in all cases. */
 #define GNODE_TRIAL_LDX 8
 int gnode_expand_trials(gnode_batch_t b, const int32_t* seeds, const int32_t* seed_ptr, const float* beta,
                         const float* gamma, float* x, int64_t ldx, void* stream);
